@@ -1,0 +1,9 @@
+"""tnqs-b200: B200-native belief-propagation simple-update engine (host mirror of the reference API).
+
+Import as `tnqs_b200` (see /tnqs_b200.py at the repo root)."""
+from . import graphs, gates  # noqa: F401
+from .graphs import (NamedGraph, named_grid, named_path_graph, named_comb_tree, eagle_heavy_hex,  # noqa: F401
+                     build_graph_from_gates, build_graph_from_circuit, edge_color,
+                     forest_cover_edge_sequence, bipartite_edge_sequence)
+from .gates import (ArgumentError, gate_matrix, observable_matrix, register_gate, register_alias,  # noqa: F401
+                    unregister_gate)

@@ -1,0 +1,228 @@
+"""Pins the CPU oracle (oracle/tnqs_oracle.py) to the reference's own test invariants
+(the reference holds no numeric goldens for this path) and to an independent
+dense state-vector simulator."""
+import math
+
+import numpy as np
+import pytest
+
+import tnqs_b200 as tq
+from oracle import tnqs_oracle as orc
+from oracle.statevector import StateVector
+
+UP, DN = (1.0, 0.0), (0.0, 1.0)
+Z = np.diag([1.0, -1.0])
+X = np.array([[0, 1], [1, 0.0]])
+Y = np.array([[0, -1j], [1j, 0]])
+
+
+def circuit_to_arrays(g, circuit):
+    mats, verts = [], []
+    for gate in circuit:
+        vs = gate[1] if isinstance(gate[1], list) else [gate[1]]
+        mats.append(tq.gate_matrix(gate[0], len(vs), gate[2] if len(gate) > 2 else None))
+        verts.append([g.index[v] for v in vs])
+    return mats, verts
+
+
+def seq_idx(g, seq):
+    return [(g.index[a], g.index[b]) for a, b in seq]
+
+
+def tfim_layer(g, dt=0.25, hx=1.0, hz=0.8, J=0.5, ncol=4):
+    layer = [("Rx", [v], 2 * hx * dt) for v in g.vertices()]
+    layer += [("Rz", [v], 2 * hz * dt) for v in g.vertices()]
+    for grp in tq.edge_color(g, ncol):
+        layer += [("Rzz", list(pair), 2 * J * dt) for pair in grp]
+    return layer
+
+
+def test_two_qubit_circuit_invariants():
+    # /root/reference/test/test_apply.jl:11-20
+    circuit = [("Rx", [(1, 1)], 0.5), ("Rx", [(2, 1)], 0.2), ("CPHASE", [(1, 1), (2, 1)], -0.3)]
+    g = tq.build_graph_from_circuit(circuit)
+    c = orc.product_state(g.nv, g.edge_uv(), [DN, DN], np.complex64)
+    seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+    c, _ = orc.bp_update(c, seq, **orc.default_bp_update_kwargs(c))
+    mats, verts = circuit_to_arrays(g, circuit)
+    c2, errs, _ = orc.apply_gates(c, mats, verts, seq,
+                                  dict(maxdim=2, cutoff=1e-10, normalize_tensors=False))
+    assert c2.dtype == np.complex64 and c2.T[0].dtype == np.complex64
+    assert c2.maxvirtualdim() <= 2
+    psi = orc.to_statevector(c2)
+    assert abs(np.vdot(psi, psi) - 1.0) < 1e-5
+    sv = StateVector([DN, DN])
+    for m, vs in zip(mats, verts):
+        sv.apply(m, vs)
+    assert abs(abs(np.vdot(sv.psi, psi)) - 1.0) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.complex64, 2e-5), (np.complex128, 1e-11)])
+def test_grid_tfim_layer_norm_and_statevector(dtype, tol):
+    # /root/reference/test/test_apply.jl:23-53 — untruncated SU on a loopy graph is exact
+    g = tq.named_grid((3, 3))
+    rng = np.random.default_rng(123)
+    locs = []
+    for _ in range(g.nv):
+        a = rng.standard_normal(2) + 1j * rng.standard_normal(2)
+        locs.append(a / np.linalg.norm(a))
+    c = orc.product_state(g.nv, g.edge_uv(), locs, dtype)
+    seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+    mats, verts = circuit_to_arrays(g, tfim_layer(g))
+    c2, errs, reps = orc.apply_gates(c, mats, verts, seq, dict(cutoff=1e-10, normalize_tensors=False))
+    assert c2.maxvirtualdim() <= 2
+    assert len(reps) == 5  # 4 colour groups + final refresh
+    assert np.all(errs < 1e-9)
+    psi = orc.to_statevector(c2)
+    assert abs(np.vdot(psi, psi) - 1.0) < 50 * tol
+    sv = StateVector(locs)
+    for m, vs in zip(mats, verts):
+        sv.apply(m, vs)
+    assert abs(abs(np.vdot(sv.psi, psi)) - 1.0) < 50 * tol
+
+
+def test_segmentation_rule():
+    # /root/reference/src/Apply/apply_gates.jl:60-90
+    g = tq.named_grid((4, 4))
+    mats, verts = circuit_to_arrays(g, tfim_layer(g))
+    fires = orc.segment_gates(verts)
+    assert len(fires) == 4
+    n1 = 2 * g.nv
+    assert fires[0] == n1  # first Rzz fires: every vertex was touched by the one-site gates
+    # inside a segment all two-site gates are vertex disjoint
+    bounds = fires + [len(verts)]
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        vs = [v for k in range(a, b) for v in verts[k]]
+        assert len(vs) == len(set(vs))
+    # one-site gate after a two-site gate on the same vertex does not fire
+    assert orc.segment_gates([[0, 1], [0], [2, 3], [1, 2]]) == [3]
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_bp_exact_on_tree(dtype):
+    # /root/reference/test/test_beliefpropagation.jl:31-55
+    g = tq.named_comb_tree((3, 3))
+    c = orc.random_state(g.nv, g.edge_uv(), 2, 2, dtype, seed=123)
+    seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+    assert len(seq) == 2 * g.ne and len(set(seq)) == 2 * g.ne
+    assert not c.msg
+    c, rep = orc.bp_update(c, seq, **orc.default_bp_update_kwargs(c))
+    assert rep["niter"] == 1 and len(c.msg) == 2 * g.ne
+    psi = orc.to_statevector(c)
+    vc = g.index[g.center()[0]]
+    rho_exact = np.moveaxis(psi, vc, 0).reshape(2, -1)
+    rho_exact = rho_exact @ rho_exact.conj().T
+    rho_exact /= np.trace(rho_exact)
+    rho_bp = orc.rdm_local(c, vc).astype(np.complex128)
+    rho_bp /= np.trace(rho_bp)
+    eps = np.finfo(np.float32 if dtype == np.complex64 else np.float64).eps
+    assert np.linalg.norm(rho_bp - rho_exact) <= 10 * eps
+
+
+def test_expect_bp_vs_exact_tree_and_loopy():
+    # /root/reference/test/test_expect.jl:10-45
+    for g, is_tree in ((tq.named_path_graph(6), True), (tq.named_grid((3, 3)), False)):
+        c = orc.random_state(g.nv, g.edge_uv(), 2, 2, np.complex128, seed=7)
+        seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+        c, _ = orc.bp_update(c, seq, maxiter=100, tolerance=1e-14)
+        psi = orc.to_statevector(c)
+        sv = StateVector([UP] * g.nv)
+        sv.psi = psi
+        v = g.nv // 2
+        e_bp = orc.expect_local(c, v, Z)
+        e_ex = sv.expect(Z, [v])
+        if is_tree:
+            assert abs(e_bp - e_ex) < 1e-12
+            w = c.incident[v][0][1]
+            assert abs(orc.expect_two_site(c, v, w, X, Y) - sv.expect(np.kron(X, Y), [v, w])) < 1e-12
+        else:
+            assert abs(e_bp - e_ex) > 1e-6
+
+
+def test_tree_dynamics_matches_statevector_with_messages_fixed_point():
+    # SU without truncation on a tree is exact, and the messages written by
+    # apply_gate! (diag σ) equal freshly recomputed BP messages up to normalisation.
+    g = tq.named_comb_tree((2, 3))
+    c = orc.product_state(g.nv, g.edge_uv(), [UP] * g.nv, np.complex128)
+    seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+    layer = [("Rx", [v], 0.7) for v in g.vertices()]
+    for grp in tq.edge_color(g, 3):
+        layer += [("Rxx", list(p), 0.9) for p in grp]
+    mats, verts = circuit_to_arrays(g, layer)
+    sv = StateVector([UP] * g.nv)
+    for _ in range(3):
+        c, errs, _ = orc.apply_gates(c, mats, verts, seq, dict(cutoff=1e-14, normalize_tensors=True))
+        for m, vs in zip(mats, verts):
+            sv.apply(m, vs)
+    for v in range(g.nv):
+        assert abs(orc.expect_local(c, v, Z) - sv.expect(Z, [v])) < 1e-10
+    # gate then compare its written messages with a recomputed BP fixed point
+    v1, v2 = c.edges[0]
+    c3 = c.copy()
+    orc.apply_gate(c3, tq.gate_matrix("Rzz", 2, 0.4), [v1, v2], cutoff=1e-14)
+    m_written = c3.msg[(v1, v2)]
+    m_bp = orc.updated_message(c3, v1, v2)
+    assert orc.message_diff(m_written, m_bp) < 1e-12
+
+
+def test_truncate_spectrum_semantics():
+    p = np.array([0.5, 0.3, 0.15, 0.04, 0.01])
+    assert orc.truncate_spectrum(p, None, None) == (5, 0.0)
+    n, e = orc.truncate_spectrum(p, 3, None)
+    assert n == 3 and abs(e - 0.05) < 1e-15
+    n, e = orc.truncate_spectrum(p, None, 0.02)  # 0.01 ≤ 0.02 dropped; 0.01+0.04 > 0.02 kept
+    assert n == 4 and abs(e - 0.01) < 1e-15
+    n, e = orc.truncate_spectrum(p, 4, 0.2)      # maxdim first, then cutoff continues: .01+.04+.15=.2 ≤ .2
+    assert n == 2 and abs(e - 0.2) < 1e-15
+    n, e = orc.truncate_spectrum(np.array([1.0, 0.0, 0.0]), None, 1e-10)
+    assert n == 1 and e == 0.0
+    n, e = orc.truncate_spectrum(np.array([0.0, 0.0]), None, 1e-10)  # mindim = 1
+    assert n == 1
+
+
+def test_truncation_maxdim_respected_and_error_positive():
+    # /root/reference/test/test_truncate.jl:29-33 flavour: χ ≤ maxdim, 0 ≤ err ≤ 1
+    g = tq.named_grid((3, 3))
+    c = orc.product_state(g.nv, g.edge_uv(), [UP] * g.nv, np.complex128)
+    seq = seq_idx(g, tq.forest_cover_edge_sequence(g))
+    mats, verts = circuit_to_arrays(g, tfim_layer(g))
+    allerrs = []
+    for _ in range(3):
+        c, errs, _ = orc.apply_gates(c, mats, verts, seq, dict(maxdim=2, cutoff=1e-12))
+        allerrs.append(errs)
+    assert c.maxvirtualdim() <= 2
+    allerrs = np.concatenate(allerrs)
+    assert np.all(allerrs >= 0) and np.all(allerrs <= 1) and allerrs.max() > 1e-8
+
+
+def test_pseudo_sqrt_inv_sqrt():
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((6, 3)) + 1j * rng.standard_normal((6, 3))
+    m = (a @ a.conj().T).astype(np.complex64)  # rank 3 PSD
+    A, B = orc.pseudo_sqrt_inv_sqrt(m, 10 * np.finfo(np.float32).eps * np.trace(m).real)
+    P = A.astype(complex) @ B.astype(complex)
+    assert np.allclose(P @ P, P, atol=1e-4) and abs(np.trace(P).real - 3) < 1e-3
+    assert np.allclose(A.astype(complex) @ A.astype(complex), m, atol=1e-4 * np.trace(m).real)
+
+
+def test_gate_conventions():
+    # Rzz(θ) = exp(-iθ/2 ZZ) after the registry's θ→θ/2 (gate_definitions.jl:49-51)
+    th = 0.37
+    zz = np.kron(Z, Z)
+    assert np.allclose(tq.gate_matrix("Rzz", 2, th), np.diag(np.exp(-0.5j * th * np.diag(zz))))
+    assert np.allclose(tq.gate_matrix("rzz", 2, th), tq.gate_matrix("Rzz", 2, th))
+    assert np.allclose(tq.gate_matrix("Rx", 1, th),
+                       math.cos(th / 2) * np.eye(2) - 1j * math.sin(th / 2) * X)
+    assert np.allclose(tq.gate_matrix("cp", 2, th), np.diag([1, 1, 1, np.exp(1j * th)]))
+    assert np.allclose(tq.gate_matrix("XZ", 2), np.kron(X, Z))
+    with pytest.raises(tq.ArgumentError):
+        tq.gate_matrix("Rzx", 2, 0.1)
+    with pytest.raises(tq.ArgumentError):
+        tq.register_gate("Rx", lambda t: np.eye(2), 1, 1)
+    with pytest.raises(tq.ArgumentError):
+        tq.gate_matrix("xx_plus_yy", 2, 0.1)
+    tq.register_gate("MyZRot", lambda t: tq.gate_matrix("Rz", 1, t), 1, 1)
+    assert np.allclose(tq.gate_matrix("MyZRot", 1, 0.3), tq.gate_matrix("Rz", 1, 0.3))
+    tq.unregister_gate("MyZRot")
+    with pytest.raises(tq.ArgumentError):
+        tq.gate_matrix("MyZRot", 1, 0.3)

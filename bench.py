@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — two-site gates/s (and BP-sweep ms) of the BP simple-update path on L×L TFIM at bond
+dimension χ (BASELINE.json metric), B200 vs the CPU reference path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--L 16] [--chi 32]
+
+A *step* is one Trotter layer of examples/2dIsing_dynamics.jl (Rx, Rz on every vertex, then the Rzz
+colour groups) applied with `apply_gates` — i.e. 2·|V| one-site gates, |E| two-site gates and
+(colours + 1) BP refreshes.  The state is evolved from the all-↑ product state for `--prep` layers
+first so that the timed layers run at saturated bond dimension χ (reported in `config`).
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "two_site_gates_per_sec"
+UNIT = "gates/s"
+
+
+def tfim_layer(tq, g, dt=0.25, hx=1.0, hz=0.8, J=0.5):
+    """examples/2dIsing_dynamics.jl:12-28."""
+    layer = [("Rx", [v], 2 * hx * dt) for v in g.vertices()]
+    layer += [("Rz", [v], 2 * hz * dt) for v in g.vertices()]
+    groups = tq.edge_color(g, 4)
+    for grp in groups:
+        layer += [("Rzz", list(pair), 2 * J * dt) for pair in grp]
+    return layer, len(groups)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks line of /opt/skills/guides/B200_PROFILING.md, sampled during the timed region."""
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm: the NumPy/OpenBLAS oracle (the Julia reference cannot run in this image)
+# ---------------------------------------------------------------------------------------------
+
+def cpu_reference_sample(L, chi, bp_iters_per_layer, ncolors, budget_s=20.0, seed=1234):
+    """Time the oracle on a bounded sample of the same workload: interior two-site gates and message
+    updates on a random χ-saturated complex64 TNS patch, extrapolated to one layer with the BP sweep
+    count the GPU run needed.  Returns (gates/s, description, ms per BP sweep)."""
+    import tnqs_b200 as tq
+    from oracle import tnqs_oracle as orc
+    try:
+        from threadpoolctl import threadpool_info
+        nthreads = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        nthreads = os.cpu_count() or 1
+    g = tq.named_grid((L, L))
+    # a 4×4 patch has interior vertices of full degree 4; interior-gate / interior-message costs are
+    # what dominate the L×L lattice
+    gp = tq.named_grid((4, 4))
+    rng = np.random.default_rng(seed)
+    c = orc.random_state(gp.nv, gp.edge_uv(), 2, chi, np.complex64, seed=seed)
+    for (u, v) in c.directed_edges():
+        n = chi
+        w = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)
+        m = w @ w.conj().T + np.eye(n, dtype=np.complex64)
+        c.msg[(u, v)] = (m / m.sum()).astype(np.complex64)
+    a, b = gp.index[(2, 2)], gp.index[(3, 2)]
+    gate = tq.gate_matrix("Rzz", 2, 0.25)
+    t_gate, n_gate = 0.0, 0
+    t0 = time.perf_counter()
+    while n_gate < 1 or (time.perf_counter() - t0 < budget_s / 2 and n_gate < 8):
+        cc = c.copy()
+        t1 = time.perf_counter()
+        orc.apply_gate(cc, gate, [a, b], maxdim=chi, cutoff=1e-10, normalize_tensors=True)
+        t_gate += time.perf_counter() - t1
+        n_gate += 1
+    t_msg, n_msg = 0.0, 0
+    t0 = time.perf_counter()
+    while n_msg < 1 or (time.perf_counter() - t0 < budget_s / 2 and n_msg < 64):
+        t1 = time.perf_counter()
+        orc.updated_message(c, a, b)
+        t_msg += time.perf_counter() - t1
+        n_msg += 1
+    tg, tm = t_gate / n_gate, t_msg / n_msg
+    layer_s = g.ne * tg + bp_iters_per_layer * 2 * g.ne * tm
+    desc = (f"oracle (NumPy/OpenBLAS, {nthreads} BLAS threads), complex64: {n_gate} interior two-site gates "
+            f"({tg*1e3:.1f} ms each) + {n_msg} interior message updates ({tm*1e3:.2f} ms each) at chi={chi}, "
+            f"extrapolated to one {L}x{L} layer = {g.ne} gates + {bp_iters_per_layer:.1f} BP sweeps x {2*g.ne} messages")
+    return g.ne / layer_s, desc, 2 * g.ne * tm * 1e3, nthreads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    desc, nthreads, sweep_ms = "", 1, 0.0
+    for i in range(args.warmup + args.steps):
+        v, desc, sweep_ms, nthreads = cpu_reference_sample(args.L, args.chi, args.ref_bp_sweeps, 4,
+                                                           budget_s=args.ref_budget)
+        if i >= args.warmup:
+            vals.append(v)
+    val = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (args.L * (args.L - 1) * 2) / val,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "c64", "data": "synthetic",
+        "config": {"workload": f"{args.L}x{args.L} square-lattice TFIM layer, chi={args.chi}, ComplexF32",
+                   "assumed_bp_sweeps_per_layer": args.ref_bp_sweeps},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": desc},
+        "bp_sweep_ms": sweep_ms,
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import tnqs_b200 as tq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU sharding of one lattice is not wired up in this revision")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; tnqs_b200 has no CPU fallback")
+    dtype = np.complex64
+    L, chi = args.L, args.chi
+    g = tq.named_grid((L, L))
+    layer, ncol = tfim_layer(tq, g)
+    n_two = g.ne
+    seq = tq.bipartite_edge_sequence(g) if args.schedule == "bipartite" else tq.forest_cover_edge_sequence(g)
+    kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
+    bp = dict(maxiter=25, tolerance=1e-5, edge_sequence=seq)  # default_bp_update_kwargs for ComplexF32
+    psi = tq.BeliefPropagationCache(tq.tensornetworkstate(dtype, lambda v: "↑", g, "S=1/2"), device=local)
+    obs = ("Z", [(L // 2 + 1, L // 2 + 1)])
+
+    t_prep = time.perf_counter()
+    for _ in range(args.prep):
+        psi, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True)
+    for _ in range(args.warmup):
+        psi, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True)
+    t_prep = time.perf_counter() - t_prep
+    bd = psi.bond_dims()
+
+    nverts, verts, mats = tq.circuit_arrays(layer, g)
+    h2d = int(nverts.nbytes + verts.nbytes + mats.nbytes)
+    psi.stats(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    sweeps, e2e_s, dev_ms, zs = 0, 0.0, 0.0, []
+    maxerr = 0.0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)  # public API, host in/out
+        z = tq.expect(psi, obs)
+        e2e_s += time.perf_counter() - t0
+        zs.append(float(np.real(z)))
+        maxerr = max(maxerr, float(errs.max()))
+        sweeps += sum(r["niter"] for r in psi.last_bp_reports)
+    st = psi.stats()
+    clocks = sampler.stop()
+    dev_ms = st["bp_ms"] + st["su_ms"]  # CUDA events on the engine stream around every apply_gates call
+    d2h = int(8 * len(nverts) + 16)
+    value = n_two * args.steps / (dev_ms * 1e-3)
+    e2e = n_two * args.steps / e2e_s
+    sweeps_per_layer = sweeps / args.steps
+    bp_sweep_ms = st["bp_ms"] / max(1, st["bp_sweeps"])
+
+    # roofline of the dominant kernel family, timed live with CUDA events (profiling mode brackets
+    # every launch group with events on the launching stream; done on one extra, untimed layer)
+    psi.set_profiling(True)
+    psi.stats(reset=True)
+    psi2, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)
+    sp = psi2.stats()
+    psi.set_profiling(False)
+    pk = peaks()
+    fam = max((("mode_product", sp["mode_ms"]), ("gram", sp["gram_ms"]), ("jacobi", sp["small_ms"])), key=lambda x: x[1])
+    # algorithmic flops of a χ-saturated layer: interior message 8·z·d·χ^{z+1}, etc. are
+    # accumulated by the engine per launch as 8·KK·MM·CC (mode product) / 8·MM²·CC (Gram)
+    roof = None
+    if "mode_flops" in sp:
+        fl = sp["mode_flops"] if fam[0] == "mode_product" else sp["gram_flops"]
+        nl = sp["mode_launches"] if fam[0] == "mode_product" else sp["gram_launches"]
+        ach = fl / (fam[1] * 1e-3) / 1e12 if fam[1] > 0 else 0.0
+        peak = pk["bf16_sustained"] / 2
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": None, "kernel": fam[0], "launches": nl,
+                "peak_note": f"TF32 dense = 1/2 of {pk['source']} sustained bf16 {pk['bf16_sustained']} TF/s (derived)",
+                "family_ms": {"mode_product": sp["mode_ms"], "gram": sp["gram_ms"], "jacobi": sp["small_ms"]}}
+
+    cpu = None
+    if not args.no_cpu:
+        v, desc, cpu_sweep_ms, nthreads = cpu_reference_sample(L, chi, sweeps_per_layer, ncol, budget_s=args.ref_budget)
+        cpu = {"value": v, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": desc, "bp_sweep_ms": cpu_sweep_ms}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "c64", "data": "synthetic",
+        "config": {"workload": f"{L}x{L} square-lattice TFIM (examples/2dIsing_dynamics.jl constants), maxdim={chi}, "
+                               f"cutoff=1e-10, ComplexF32, one Trotter layer per step = {n_two} two-site + {2*g.nv} one-site "
+                               f"gates + {ncol+1} BP refreshes",
+                   "prep_layers": args.prep, "bond_dim_min_mean_max": [int(bd.min()), float(bd.mean()), int(bd.max())],
+                   "bp_schedule": args.schedule, "bp_sweeps_per_layer": sweeps_per_layer,
+                   "l2": "inputs larger than L2 (state %.2f GB)" % (sum(2 * int(np.prod([2] + [bd[e] for e, _ in g.incident[i]])) * 4
+                                                                     for i in range(g.nv)) / 1e9),
+                   "max_trunc_err": maxerr, "sz_center": zs},
+        "bp_sweep_ms": bp_sweep_ms,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "prep_seconds": t_prep,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=16)
+    ap.add_argument("--chi", type=int, default=32)
+    ap.add_argument("--prep", type=int, default=6, help="untimed layers from the product state before warm-up")
+    ap.add_argument("--schedule", default="bipartite", choices=["bipartite", "forest"])
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=20.0)
+    ap.add_argument("--ref-bp-sweeps", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,459 @@
+"""Host mirror of the reference's Julia surface for the BP simple-update path, over the C-ABI.
+
+Same names, argument meaning and error behaviour as the reference functions that
+`/root/reference/examples/2dIsing_dynamics.jl` calls:
+
+    tensornetworkstate / random_tensornetworkstate   src/TensorNetworks/tensornetworkstate.jl:93-161
+    BeliefPropagationCache(ψ)                         src/MessagePassing/beliefpropagationcache.jl:27-31
+    apply_gates / apply_circuit                       src/Apply/apply_gates.jl:17-98,145
+    update                                            src/MessagePassing/abstractbeliefpropagationcache.jl:223-259
+    expect                                            src/expect.jl:54-82,114-135
+    network / maxvirtualdim / messages / message      beliefpropagationcache.jl:23-25, abstracttensornetwork.jl:27-29
+
+All numerics run on the GPU behind `libtnqs_b200.so`; this module only marshals.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Dict, Hashable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .gates import STATES, ArgumentError, gate_matrix, observable_matrix
+from .graphs import NamedGraph, _as_vertex_list, forest_cover_edge_sequence
+
+_DT = {np.dtype(np.complex64): _lib.TNQS_C64, np.dtype(np.complex128): _lib.TNQS_C128}
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class TensorNetworkState:
+    """Host-resident TNS: `graph` + one numpy tensor `(d, χ_leg0, χ_leg1, …)` per vertex, bond legs
+    in increasing edge id (`tensornetworkstate.jl:12-15`)."""
+
+    def __init__(self, graph: NamedGraph, tensors: Dict[Hashable, np.ndarray], dtype=None):
+        self.graph = graph
+        dtype = np.dtype(dtype if dtype is not None else next(iter(tensors.values())).dtype)
+        if dtype not in _DT:
+            raise ArgumentError("tnqs_b200 supports ComplexF32 (complex64) and ComplexF64 (complex128) states")
+        self.dtype = dtype
+        self.tensors = {v: np.ascontiguousarray(tensors[v], dtype=dtype) for v in graph.vertices()}
+        for v in graph.vertices():
+            if self.tensors[v].ndim != 1 + graph.degree(v):
+                raise ArgumentError(f"tensor on vertex {v} must have 1 + degree indices")
+
+    def __getitem__(self, v):
+        return self.tensors[v]
+
+    def vertices(self):
+        return self.graph.vertices()
+
+    def scalartype(self):
+        return self.dtype
+
+    def maxvirtualdim(self) -> int:
+        return max((max(t.shape[1:], default=1) for t in self.tensors.values()), default=1)
+
+
+def tensornetworkstate(eltype, f, g: NamedGraph, sitetype: str = "S=1/2") -> TensorNetworkState:
+    """Product state: `f(v)` is a state name ("↑", "↓", "0", "1", "+", …) or a vector
+    (`tensornetworkstate.jl:141-161`)."""
+    if sitetype not in ("S=1/2", "Qubit", "S=½"):
+        raise ArgumentError("only spin-1/2 / qubit sites are supported on the device path")
+    tensors = {}
+    for v in g.vertices():
+        s = f(v)
+        if isinstance(s, str):
+            if s not in STATES:
+                raise ArgumentError(f'Unrecognized local state "{s}"')
+            vec = np.array(STATES[s], dtype=eltype)
+        elif isinstance(s, (list, tuple, np.ndarray)):
+            vec = np.asarray(s, dtype=eltype)
+        else:
+            raise ArgumentError("Unrecognized local state constructor. Currently supported: Strings and Vectors.")
+        tensors[v] = vec.reshape((-1,) + (1,) * g.degree(v))
+    return TensorNetworkState(g, tensors, eltype)
+
+
+def zerostate(eltype, g: NamedGraph) -> TensorNetworkState:
+    return tensornetworkstate(eltype, lambda v: "↑", g)
+
+
+def random_tensornetworkstate(eltype, g: NamedGraph, bond_dimension: int = 1, d: int = 2, seed=None) -> TensorNetworkState:
+    """iid normal entries (`tensornetworkstate.jl:93-103`); the RNG stream is NumPy's."""
+    rng = np.random.default_rng(seed)
+    tensors = {}
+    for v in g.vertices():
+        shp = (d,) + (bond_dimension,) * g.degree(v)
+        t = rng.standard_normal(shp) + 1j * rng.standard_normal(shp)
+        tensors[v] = t.astype(eltype)
+    return TensorNetworkState(g, tensors, eltype)
+
+
+class BeliefPropagationCache:
+    """Device-resident `BeliefPropagationCache` (`beliefpropagationcache.jl:9-15`): site tensors and
+    messages live in HBM behind a `tnqs_handle`; constructing it runs no BP and leaves every message
+    at its identity default."""
+
+    def __init__(self, psi: TensorNetworkState, device: int = 0, _handle=None, _graph=None, _dtype=None,
+                 _seq=None):
+        self._lib = _lib.load()
+        if _handle is not None:
+            self._h, self.graph, self.dtype, self._seq = _handle, _graph, _dtype, _seq
+            self.device = device
+            return
+        g = psi.graph
+        self.graph, self.dtype, self.device = g, psi.dtype, device
+        uv = np.array(g.edge_uv(), dtype=np.int32).reshape(-1, 2)
+        phys = np.array([psi.tensors[v].shape[0] for v in g.vertices()], dtype=np.int32)
+        bond = np.ones(g.ne, dtype=np.int32)
+        for i, v in enumerate(g.vertices()):
+            for k, (e, _) in enumerate(g.incident[i]):
+                bond[e] = psi.tensors[v].shape[1 + k]
+        h = C.c_void_p()
+        uv_a, uv_p = _i32(uv)
+        ph_a, ph_p = _i32(phys)
+        bo_a, bo_p = _i32(bond)
+        _lib.check(self._lib.tnqs_create(_DT[psi.dtype], g.nv, g.ne, uv_p, ph_p, bo_p, device, C.byref(h)))
+        self._h = h
+        for i, v in enumerate(g.vertices()):
+            t = psi.tensors[v]
+            shp = np.array(t.shape, dtype=np.int64)
+            _lib.check(self._lib.tnqs_set_site(self._h, i, t.ctypes.data_as(C.c_void_p), t.ndim,
+                                               shp.ctypes.data_as(C.POINTER(C.c_int64))))
+        self._seq = None
+        self.set_edge_sequence(forest_cover_edge_sequence(g))
+
+    # -- lifetime ---------------------------------------------------------------------------------
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.tnqs_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def copy(self) -> "BeliefPropagationCache":
+        """`Base.copy` (`beliefpropagationcache.jl:35-37`) — a device-to-device clone."""
+        h = C.c_void_p()
+        _lib.check(self._lib.tnqs_clone(self._h, C.byref(h)))
+        return BeliefPropagationCache(None, self.device, _handle=h, _graph=self.graph, _dtype=self.dtype,
+                                      _seq=self._seq)
+
+    # -- accessors --------------------------------------------------------------------------------
+    def set_edge_sequence(self, seq: Sequence[Tuple[Hashable, Hashable]]):
+        idx = np.array([[self.graph.index[a], self.graph.index[b]] for a, b in seq], dtype=np.int32).reshape(-1, 2)
+        a, p = _i32(idx)
+        _lib.check(self._lib.tnqs_set_edge_sequence(self._h, p, len(idx)))
+        self._seq = list(seq)
+
+    def edge_sequence(self):
+        return list(self._seq)
+
+    def scalartype(self):
+        return self.dtype
+
+    def vertices(self):
+        return self.graph.vertices()
+
+    def bond_dims(self) -> np.ndarray:
+        out = np.zeros(self.graph.ne, dtype=np.int32)
+        _lib.check(self._lib.tnqs_get_bond_dims(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def maxvirtualdim(self) -> int:
+        """`maxvirtualdim` (`abstracttensornetwork.jl:27-29`)."""
+        b = self.bond_dims()
+        return int(b.max()) if len(b) else 1
+
+    def site(self, v) -> np.ndarray:
+        """`network(ψ_bpc)[v]`: download one site tensor."""
+        i = self.graph.index[v]
+        nd = C.c_int(64)
+        shp = (C.c_int64 * 64)()
+        _lib.check(self._lib.tnqs_site_shape(self._h, i, C.byref(nd), shp))
+        shape = tuple(int(shp[k]) for k in range(nd.value))
+        out = np.empty(shape, dtype=self.dtype)
+        _lib.check(self._lib.tnqs_get_site(self._h, i, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
+    def network(self) -> TensorNetworkState:
+        """`network(ψ_bpc)` (`beliefpropagationcache.jl:24`): materialise the TNS on the host."""
+        return TensorNetworkState(self.graph, {v: self.site(v) for v in self.graph.vertices()}, self.dtype)
+
+    def message(self, edge) -> np.ndarray:
+        """`message(bpc, src => dst)` with the identity default (`abstractbeliefpropagationcache.jl:99-102`)."""
+        m, _ = self._message(edge)
+        return m
+
+    def _message(self, edge):
+        a, b = edge
+        chi = int(self.bond_dims()[self.graph.edge_id(a, b)])
+        out = np.empty((chi, chi), dtype=self.dtype)
+        c, s = C.c_int(), C.c_int()
+        _lib.check(self._lib.tnqs_get_message(self._h, self.graph.index[a], self.graph.index[b],
+                                              out.ctypes.data_as(C.c_void_p), out.size, C.byref(c), C.byref(s)))
+        return out, bool(s.value)
+
+    def messages(self) -> Dict[Tuple[Hashable, Hashable], np.ndarray]:
+        """`messages(bpc)`: only messages that have been set (empty right after construction)."""
+        out = {}
+        for (a, b) in self.graph.edges:
+            for e in ((a, b), (b, a)):
+                m, is_set = self._message(e)
+                if is_set:
+                    out[e] = m
+        return out
+
+    def setmessage(self, edge, m: np.ndarray):
+        a, b = edge
+        m = np.ascontiguousarray(m, dtype=self.dtype)
+        _lib.check(self._lib.tnqs_set_message(self._h, self.graph.index[a], self.graph.index[b],
+                                              m.ctypes.data_as(C.c_void_p), m.shape[0]))
+        return self
+
+    def setmessages(self, edges, ms):
+        for e, m in zip(edges, ms):
+            self.setmessage(e, m)
+        return self
+
+    def stats(self, reset: bool = False) -> dict:
+        s = _lib.Stats()
+        _lib.check(self._lib.tnqs_get_stats(self._h, C.byref(s), int(reset)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+    def set_profiling(self, on: bool):
+        _lib.check(self._lib.tnqs_set_profiling(self._h, int(on)))
+
+
+# ---------------------------------------------------------------------------------------------
+# kwargs → C structs
+# ---------------------------------------------------------------------------------------------
+
+def _apply_opts(kw: Optional[dict]) -> _lib.ApplyOpts:
+    kw = dict(kw or {})
+    o = _lib.ApplyOpts(0, 1, -1.0, 1, -1.0)
+    for k, v in kw.items():
+        if k == "maxdim":
+            o.maxdim = int(v) if v is not None else 0
+        elif k == "mindim":
+            o.mindim = int(v)
+        elif k == "cutoff":
+            o.cutoff = float(v) if v is not None else -1.0
+        elif k == "normalize_tensors":
+            o.normalize_tensors = int(bool(v))
+        elif k == "sqrt_cutoff":
+            o.sqrt_cutoff = float(v) if v is not None else -1.0
+        else:
+            raise ArgumentError(f"unsupported apply keyword {k!r} (supported: maxdim, mindim, cutoff, "
+                                "normalize_tensors, sqrt_cutoff)")
+    return o
+
+
+def default_bp_update_kwargs(bpc) -> dict:
+    """`default_bp_update_kwargs` (`beliefpropagationcache.jl:110-119`)."""
+    if bpc.graph.is_tree():
+        return dict(maxiter=1, tolerance=None, verbose=False)
+    return dict(maxiter=25, tolerance=1e-5 if np.dtype(bpc.dtype) == np.complex64 else 1e-8, verbose=False)
+
+
+def _bp_opts(bpc: BeliefPropagationCache, kw: Optional[dict]):
+    base = default_bp_update_kwargs(bpc) if kw is None else dict(kw)
+    keep = []
+    o = _lib.BpOpts(0, -1.0, 0, None, 0)
+    maxiter = base.get("maxiter", None)
+    if maxiter is None:
+        maxiter = 1 if bpc.graph.is_tree() else 25  # default_bp_maxiter, beliefpropagationcache.jl:39
+    o.maxiter = int(maxiter)
+    tol = base.get("tolerance", None)  # default_tolerance(::Algorithm"bp") = nothing (:54)
+    if tol is not None:
+        o.use_tolerance, o.tolerance = 1, float(tol)
+    seq = base.get("edge_sequence", None)
+    if seq is not None:
+        idx = np.array([[bpc.graph.index[a], bpc.graph.index[b]] for a, b in seq], dtype=np.int32).reshape(-1, 2)
+        a, p = _i32(idx)
+        keep.append(a)
+        o.edge_sequence, o.n_seq = p, len(idx)
+    unknown = set(base) - {"maxiter", "tolerance", "verbose", "edge_sequence"}
+    if unknown:
+        raise ArgumentError(f"unsupported BP keyword(s) {sorted(unknown)}")
+    return o, keep, bool(base.get("verbose", False)), tol
+
+
+def _report_bp(rep, tol, verbose):
+    """Same text as `abstractbeliefpropagationcache.jl:245-252`."""
+    if tol is None:
+        return
+    if rep.converged:
+        if verbose:
+            print(f"BP converged to desired precision after {rep.niter} iterations.")
+    else:
+        msg = (f"BP did not converge to tolerance {tol} after {rep.niter} iterations "
+               f"(final average message change: {rep.diff}).")
+        print(msg) if verbose else warnings.warn(msg)
+
+
+# ---------------------------------------------------------------------------------------------
+# the public functions
+# ---------------------------------------------------------------------------------------------
+
+def update(bpc: BeliefPropagationCache, inplace: bool = False, **kwargs) -> BeliefPropagationCache:
+    """`update(bpc; maxiter, tolerance, verbose, edge_sequence)` → updated copy
+    (`abstractbeliefpropagationcache.jl:257-259`).  Keywords left out take the `Algorithm"bp"`
+    defaults of `beliefpropagationcache.jl:52-72`: maxiter 25 (1 on trees), tolerance `nothing`."""
+    out = bpc if inplace else bpc.copy()
+    o, keep, verbose, tol = _bp_opts(out, kwargs)
+    rep = _lib.BpReport()
+    _lib.check(out._lib.tnqs_bp_update(out._h, C.byref(o), C.byref(rep)))
+    _report_bp(rep, tol, verbose)
+    out.last_bp_report = dict(niter=rep.niter, converged=bool(rep.converged), diff=rep.diff)
+    return out
+
+
+def circuit_arrays(circuit: Sequence, g: NamedGraph):
+    """`toitensor(circuit, g, siteinds)` (`gate_definitions.jl:110-153`) down to flat arrays."""
+    nverts, verts, mats = [], [], []
+    for gate in circuit:
+        if isinstance(gate, tuple) and len(gate) >= 2:
+            vs = _as_vertex_list(gate[1])
+            for v in vs:
+                if v not in g.index:
+                    raise ArgumentError(f"gate vertex {v!r} is not a vertex of the graph")
+            m = gate_matrix(gate[0], len(vs), gate[2] if len(gate) > 2 else None)
+        else:
+            raise ArgumentError("circuit entries must be (name_or_matrix, vertices[, params]) tuples")
+        nverts.append(len(vs))
+        idx = [g.index[v] for v in vs]
+        verts.append((idx + [-1, -1])[:2] if len(idx) <= 2 else idx[:2])
+        mats.append(np.asarray(m, dtype=np.complex128).reshape(-1))
+    mats = np.concatenate(mats) if mats else np.zeros(0, dtype=np.complex128)
+    return (np.array(nverts, dtype=np.int32), np.array(verts, dtype=np.int32).reshape(-1, 2),
+            np.ascontiguousarray(mats).view(np.float64))
+
+
+def apply_gates(circuit: Sequence, psi, apply_kwargs: Optional[dict] = None,
+                bp_update_kwargs: Optional[dict] = None, update_cache: bool = True, verbose: bool = False,
+                inplace: bool = False, device: int = 0):
+    """`apply_gates(circuit, ψ | ψ_bpc; apply_kwargs, bp_update_kwargs, update_cache, verbose)`
+    → `(ψ′, errs)` (`apply_gates.jl:17-98`).  The input cache is not mutated unless `inplace=True`
+    (an extension: the examples rebind the result, so in-place is observationally the same)."""
+    if isinstance(psi, TensorNetworkState):  # apply_gates.jl:17-27
+        bpc = BeliefPropagationCache(psi, device=device)
+        kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(bpc)
+        bpc = update(bpc, inplace=True, **kw)
+        bpc, errs = apply_gates(circuit, bpc, apply_kwargs, kw, update_cache, verbose, inplace=True)
+        return bpc.network(), errs
+    bpc: BeliefPropagationCache = psi
+    nverts, verts, mats = circuit_arrays(circuit, bpc.graph)
+    out = bpc if inplace else bpc.copy()
+    ao = _apply_opts(apply_kwargs)
+    bo, keep, bverbose, tol = _bp_opts(out, bp_update_kwargs)
+    ng = len(nverts)
+    errs = np.zeros(ng, dtype=np.float64)
+    max_rep = ng + 1
+    reps = (_lib.BpReport * max_rep)()
+    nrep = C.c_int(0)
+    nv_a, nv_p = _i32(nverts)
+    vs_a, vs_p = _i32(verts)
+    m_a, m_p = _f64(mats)
+    _lib.check(out._lib.tnqs_apply_gates(out._h, ng, nv_p, vs_p, m_p, C.byref(ao), C.byref(bo), int(update_cache),
+                                         errs.ctypes.data_as(C.POINTER(C.c_double)), reps, max_rep, C.byref(nrep)))
+    out.last_bp_reports = [dict(niter=reps[i].niter, converged=bool(reps[i].converged), diff=reps[i].diff)
+                           for i in range(min(nrep.value, max_rep))]
+    for i in range(min(nrep.value, max_rep)):
+        if verbose:
+            print("Updating BP cache")
+        _report_bp(reps[i], tol, bverbose or verbose)
+    return out, errs
+
+
+apply_circuit = apply_gates
+
+
+def _collect_observable(obs, g: NamedGraph):
+    """`collectobservable` (`expect.jl:159-175`)."""
+    coeff = 1 if len(obs) == 2 else obs[-1]
+    verts = _as_vertex_list(obs[1])
+    op = obs[0]
+    if isinstance(op, str):
+        ops = [c for c in op]
+    elif isinstance(op, (list, tuple)) and all(isinstance(o, str) for o in op):
+        ops = list(op)
+    else:
+        raise RuntimeError("Invalid observable, did not recognize operator specification. Either a single "
+                           "string (one pauli character per vertex) or a vector of strings (one string per "
+                           "vertex) expected.")
+    if len(ops) != len(verts):
+        raise RuntimeError("Invalid observable: need as many operators as vertices passed.")
+    return ops, verts, coeff
+
+
+def expect(psi, observable, alg: Optional[str] = "bp", **cache_update_kwargs):
+    """`expect(ψ | ψ_bpc, obs; alg="bp")` (`expect.jl:54-82,114-135`).  `obs = (ops, vertices[,
+    coeff])` or a list of them.  Device path: single-site and adjacent two-site observables."""
+    if alg != "bp":
+        raise RuntimeError("Expected alg = \"bp\": exact and boundary-MPS contraction are outside the "
+                           "accelerated path (export with network(ψ_bpc) and use the reference for those)")
+    if isinstance(psi, TensorNetworkState):  # expect.jl:123-135
+        bpc = BeliefPropagationCache(psi)
+        kw = cache_update_kwargs or default_bp_update_kwargs(bpc)
+        bpc = update(bpc, inplace=True, **kw)
+        return expect(bpc, observable, alg)
+    bpc: BeliefPropagationCache = psi
+    single = isinstance(observable, tuple)
+    obs_list = [observable] if single else list(observable)
+    out: List = [None] * len(obs_list)
+    one, two = [], []
+    for i, obs in enumerate(obs_list):
+        ops, verts, coeff = _collect_observable(obs, bpc.graph)
+        if coeff == 0:
+            out[i] = 0 * coeff
+        elif len(verts) == 1:
+            one.append((i, ops, verts, coeff))
+        elif len(verts) == 2 and bpc.graph.has_edge(verts[0], verts[1]):
+            two.append((i, ops, verts, coeff))
+        else:
+            raise NotImplementedError("device expect supports single-site and adjacent two-site observables")
+    lib = bpc._lib
+    if one:
+        vs_a, vs_p = _i32([bpc.graph.index[o[2][0]] for o in one])
+        m_a, m_p = _f64(np.concatenate([observable_matrix(o[1][0]).reshape(-1) for o in one]).view(np.float64))
+        res = np.zeros(2 * len(one))
+        _lib.check(lib.tnqs_expect_local(bpc._h, len(one), vs_p, m_p, res.ctypes.data_as(C.POINTER(C.c_double))))
+        for k, o in enumerate(one):
+            out[o[0]] = o[3] * complex(res[2 * k], res[2 * k + 1])
+    if two:
+        vs_a, vs_p = _i32([[bpc.graph.index[v] for v in o[2]] for o in two])
+        m_a, m_p = _f64(np.concatenate([observable_matrix(c).reshape(-1) for o in two for c in o[1]]).view(np.float64))
+        res = np.zeros(2 * len(two))
+        _lib.check(lib.tnqs_expect_two_site(bpc._h, len(two), vs_p, m_p, res.ctypes.data_as(C.POINTER(C.c_double))))
+        for k, o in enumerate(two):
+            out[o[0]] = o[3] * complex(res[2 * k], res[2 * k + 1])
+    return out[0] if single else out
+
+
+def network(bpc: BeliefPropagationCache) -> TensorNetworkState:
+    return bpc.network()
+
+
+def maxvirtualdim(x) -> int:
+    return x.maxvirtualdim()
+
+
+def messages(bpc: BeliefPropagationCache):
+    return bpc.messages()
+
+
+def message(bpc: BeliefPropagationCache, edge):
+    return bpc.message(edge)

@@ -1,0 +1,1202 @@
+// engine.cu — implementation of the host-side engine (see engine.cuh).
+#include "engine.cuh"
+
+#include <cstdio>
+#include <numeric>
+#include <set>
+
+namespace tnqs {
+
+using cplx = std::complex<double>;
+
+// ------------------------------------------------------------------------------------------------
+// construction / destruction
+// ------------------------------------------------------------------------------------------------
+Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t* phys,
+               const int32_t* bond, int device)
+    : dtype_(dtype), esz_(dtype == TNQS_C64 ? 8 : 16), device_(device), nv_(nv), ne_(ne) {
+  if (dtype != TNQS_C64 && dtype != TNQS_C128) throw Error(TNQS_EINVAL, "dtype must be TNQS_C64 or TNQS_C128");
+  if (nv <= 0 || ne < 0) throw Error(TNQS_EINVAL, "need nv > 0, ne >= 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    throw Error(TNQS_ENOGPU, "no CUDA device visible: tnqs_b200 has no CPU fallback");
+  if (device < 0 || device >= ndev) throw Error(TNQS_EINVAL, "bad CUDA device ordinal");
+  TNQS_CUDA(cudaSetDevice(device));
+  eu_.resize(ne); ev_.resize(ne); bond_.resize(ne); phys_.assign(phys, phys + nv);
+  inc_.assign(nv, {});
+  std::set<std::pair<int, int>> seen;
+  for (int e = 0; e < ne; ++e) {
+    const int u = edge_uv[2 * e], v = edge_uv[2 * e + 1];
+    if (u < 0 || v < 0 || u >= nv || v >= nv || u == v) throw Error(TNQS_EINVAL, "bad edge endpoints");
+    if (!seen.insert({std::min(u, v), std::max(u, v)}).second) throw Error(TNQS_EINVAL, "duplicate edge");
+    if (bond[e] < 1) throw Error(TNQS_EINVAL, "bond dimension must be >= 1");
+    eu_[e] = u; ev_[e] = v; bond_[e] = bond[e];
+    inc_[u].push_back({e, v});
+    inc_[v].push_back({e, u});
+  }
+  for (int v = 0; v < nv; ++v)
+    if (phys_[v] < 1 || phys_[v] > 4) throw Error(TNQS_EINVAL, "physical dimension must be in 1..4");
+  // tree test (default_bp_maxiter, beliefpropagationcache.jl:39)
+  {
+    std::vector<char> vis(nv, 0);
+    std::vector<int> st{0};
+    vis[0] = 1;
+    int cnt = 1;
+    while (!st.empty()) {
+      const int x = st.back(); st.pop_back();
+      for (auto& l : inc_[x]) if (!vis[l.nbr]) { vis[l.nbr] = 1; ++cnt; st.push_back(l.nbr); }
+    }
+    is_tree_ = (cnt == nv) && (ne == nv - 1);
+  }
+  TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  TNQS_CUDA(cudaEventCreate(&ev0_));
+  TNQS_CUDA(cudaEventCreate(&ev1_));
+  cudaMemPool_t pool;
+  TNQS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  TNQS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  site_.assign(nv, nullptr);
+  sshape_.assign(nv, {});
+  for (int v = 0; v < nv; ++v) {
+    sshape_[v].clear();
+    for (auto& l : inc_[v]) sshape_[v].push_back(bond_[l.edge]);
+    const long long n = site_elems(v);
+    site_[v] = dalloc((size_t)n * esz_);
+    TNQS_CUDA(cudaMemsetAsync(site_[v], 0, (size_t)n * esz_, stream_));
+    if (c64()) { const float one[2] = {1.f, 0.f}; TNQS_CUDA(cudaMemcpyAsync(site_[v], one, 8, cudaMemcpyHostToDevice, stream_)); }
+    else { const double one[2] = {1.0, 0.0}; TNQS_CUDA(cudaMemcpyAsync(site_[v], one, 16, cudaMemcpyHostToDevice, stream_)); }
+  }
+  msg_.assign(2 * ne, nullptr);
+  msg_next_.assign(2 * ne, nullptr);
+  msg_dim_.assign(2 * ne, 0);
+  msg_next_dim_.assign(2 * ne, 0);
+  msg_set_.assign(2 * ne, 0);
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+
+Engine::Engine(const Engine& o)
+    : dtype_(o.dtype_), esz_(o.esz_), device_(o.device_), nv_(o.nv_), ne_(o.ne_), eu_(o.eu_), ev_(o.ev_),
+      phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  TNQS_CUDA(cudaEventCreate(&ev0_));
+  TNQS_CUDA(cudaEventCreate(&ev1_));
+  TNQS_CUDA(cudaStreamSynchronize(o.stream_));
+  site_.assign(nv_, nullptr);
+  for (int v = 0; v < nv_; ++v) {
+    const size_t b = (size_t)site_elems(v) * esz_;
+    site_[v] = dalloc(b);
+    TNQS_CUDA(cudaMemcpyAsync(site_[v], o.site_[v], b, cudaMemcpyDeviceToDevice, stream_));
+  }
+  msg_.assign(2 * ne_, nullptr);
+  msg_next_.assign(2 * ne_, nullptr);
+  msg_dim_ = o.msg_dim_;
+  msg_next_dim_.assign(2 * ne_, 0);
+  msg_set_ = o.msg_set_;
+  for (int de = 0; de < 2 * ne_; ++de) {
+    if (!o.msg_[de] || !o.msg_dim_[de]) { msg_dim_[de] = 0; continue; }
+    const size_t b = (size_t)msg_dim_[de] * msg_dim_[de] * esz_;
+    msg_[de] = dalloc(b);
+    TNQS_CUDA(cudaMemcpyAsync(msg_[de], o.msg_[de], b, cudaMemcpyDeviceToDevice, stream_));
+  }
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (void* p : temps_) cudaFreeAsync(p, stream_);
+  for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
+  for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
+  for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
+  if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
+  if (ev0_) cudaEventDestroy(ev0_);
+  if (ev1_) cudaEventDestroy(ev1_);
+}
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+void* Engine::dalloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  TNQS_CUDA(cudaMallocAsync(&p, bytes, stream_));
+  return p;
+}
+void* Engine::talloc(size_t bytes) {
+  void* p = dalloc(bytes);
+  temps_.push_back(p);
+  return p;
+}
+void Engine::dfree(void* p) {
+  if (p) TNQS_CUDA(cudaFreeAsync(p, stream_));
+}
+void Engine::free_temps() {
+  for (void* p : temps_) TNQS_CUDA(cudaFreeAsync(p, stream_));
+  temps_.clear();
+}
+template <class T> T* Engine::upload(const std::vector<T>& v) {
+  T* d = (T*)talloc(v.size() * sizeof(T));
+  if (!v.empty())
+    TNQS_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream_));
+  return d;
+}
+int Engine::dedge(int src, int dst) const {
+  if (src < 0 || src >= nv_ || dst < 0 || dst >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+  for (auto& l : inc_[src])
+    if (l.nbr == dst) return 2 * l.edge + (eu_[l.edge] == src ? 0 : 1);
+  throw Error(TNQS_ENOTADJ, "vertices " + std::to_string(src) + " and " + std::to_string(dst) + " do not share an edge");
+}
+int Engine::leg_pos(int v, int e) const {
+  for (size_t k = 0; k < inc_[v].size(); ++k) if (inc_[v][k].edge == e) return (int)k;
+  throw Error(TNQS_EINVAL, "edge not incident to vertex");
+}
+long long Engine::site_elems(int v) const {
+  long long n = phys_[v];
+  for (auto& l : inc_[v]) n *= bond_[l.edge];
+  return n;
+}
+// view of T_v around bond leg `pos` with the physical index folded into `outer`;
+// pos == -1 selects the physical index itself.
+void Engine::leg_view(int v, int pos, unsigned* outer, int* chi, unsigned* inner) const {
+  long long o = 1, in = 1;
+  const int z = (int)inc_[v].size();
+  if (pos < 0) {
+    for (int k = 0; k < z; ++k) in *= bond_[inc_[v][k].edge];
+    *chi = phys_[v];
+  } else {
+    o = phys_[v];
+    for (int k = 0; k < pos; ++k) o *= bond_[inc_[v][k].edge];
+    for (int k = pos + 1; k < z; ++k) in *= bond_[inc_[v][k].edge];
+    *chi = bond_[inc_[v][pos].edge];
+  }
+  if (o * in >= (1ll << 31) || o >= (1ll << 31) || in >= (1ll << 31))
+    throw Error(TNQS_EINVAL, "site tensor too large for 32-bit column indexing");
+  *outer = (unsigned)o; *inner = (unsigned)in;
+}
+void Engine::check_shapes() const {
+  for (int v = 0; v < nv_; ++v)
+    for (size_t k = 0; k < inc_[v].size(); ++k)
+      if (sshape_[v][k] != bond_[inc_[v][k].edge])
+        throw Error(TNQS_EINVAL, "site " + std::to_string(v) + " leg " + std::to_string(k) +
+                                     " disagrees with the bond dimension of its edge (set both endpoint tensors)");
+}
+void Engine::materialize_message(int de) {
+  const int chi = bond_[de / 2];
+  if (msg_[de] && msg_dim_[de] == chi) return;
+  if (msg_[de]) dfree(msg_[de]);
+  msg_[de] = dalloc((size_t)chi * chi * esz_);
+  msg_dim_[de] = chi;
+  msg_set_[de] = 0;
+  std::vector<DiagTask> t(1);
+  t[0].out = msg_[de]; t[0].chi = chi; t[0].diag = nullptr; t[0].scale_sumsq = nullptr;
+  DiagTask* d = upload(t);
+  const int nb = std::min(64, (chi * chi + 255) / 256);
+  if (c64()) diag_fill_kernel<float><<<dim3(nb, 1), 256, 0, stream_>>>(d);
+  else diag_fill_kernel<double><<<dim3(nb, 1), 256, 0, stream_>>>(d);
+  count_launch();
+}
+size_t Engine::scratch_budget() const {
+  size_t fr = 0, tot = 0;
+  cudaMemGetInfo(&fr, &tot);
+  cudaMemPool_t pool;
+  uint64_t reserved = 0, used = 0;
+  if (cudaDeviceGetDefaultMemPool(&pool, device_) == cudaSuccess) {
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+  }
+  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0);
+  return (size_t)(0.7 * (double)avail);
+}
+
+// ------------------------------------------------------------------------------------------------
+// import / export
+// ------------------------------------------------------------------------------------------------
+void Engine::set_site(int v, const void* data, int ndim, const int64_t* shape) {
+  if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+  const int z = (int)inc_[v].size();
+  if (ndim != z + 1) throw Error(TNQS_EINVAL, "site tensor must have 1 + degree indices");
+  if (shape[0] != phys_[v]) throw Error(TNQS_EINVAL, "physical dimension mismatch");
+  TNQS_CUDA(cudaSetDevice(device_));
+  for (int k = 0; k < z; ++k) {
+    if (shape[1 + k] < 1) throw Error(TNQS_EINVAL, "bond dimension must be >= 1");
+    const int e = inc_[v][k].edge;
+    if (bond_[e] != (int)shape[1 + k]) {
+      bond_[e] = (int)shape[1 + k];
+      for (int de = 2 * e; de < 2 * e + 2; ++de) {  // messages on a resized bond fall back to the default
+        if (msg_[de]) { dfree(msg_[de]); msg_[de] = nullptr; }
+        msg_dim_[de] = 0; msg_set_[de] = 0;
+      }
+    }
+    sshape_[v][k] = (int)shape[1 + k];
+  }
+  dfree(site_[v]);
+  const size_t b = (size_t)site_elems(v) * esz_;
+  site_[v] = dalloc(b);
+  TNQS_CUDA(cudaMemcpyAsync(site_[v], data, b, cudaMemcpyHostToDevice, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::site_shape(int v, int* ndim, int64_t* shape) const {
+  if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+  const int z = (int)inc_[v].size();
+  if (*ndim < z + 1) throw Error(TNQS_ECAPACITY, "shape buffer too small");
+  *ndim = z + 1;
+  shape[0] = phys_[v];
+  for (int k = 0; k < z; ++k) shape[1 + k] = sshape_[v][k];
+}
+void Engine::get_site(int v, void* data, int64_t cap) {
+  if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+  long long n = phys_[v];
+  for (int x : sshape_[v]) n *= x;
+  if (cap < n) throw Error(TNQS_ECAPACITY, "site buffer too small");
+  TNQS_CUDA(cudaSetDevice(device_));
+  TNQS_CUDA(cudaMemcpyAsync(data, site_[v], (size_t)n * esz_, cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::set_message(int src, int dst, const void* data, int chi) {
+  const int de = dedge(src, dst);
+  if (chi != bond_[de / 2]) throw Error(TNQS_EINVAL, "message dimension must equal the bond dimension");
+  TNQS_CUDA(cudaSetDevice(device_));
+  if (msg_[de] && msg_dim_[de] != chi) { dfree(msg_[de]); msg_[de] = nullptr; }
+  if (!msg_[de]) msg_[de] = dalloc((size_t)chi * chi * esz_);
+  msg_dim_[de] = chi;
+  msg_set_[de] = 1;
+  TNQS_CUDA(cudaMemcpyAsync(msg_[de], data, (size_t)chi * chi * esz_, cudaMemcpyHostToDevice, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+void Engine::get_message(int src, int dst, void* out, int64_t cap, int* chi, int* is_set) {
+  const int de = dedge(src, dst);
+  TNQS_CUDA(cudaSetDevice(device_));
+  materialize_message(de);
+  const int n = msg_dim_[de];
+  *chi = n;
+  *is_set = msg_set_[de];
+  if (cap < (int64_t)n * n) throw Error(TNQS_ECAPACITY, "message buffer too small");
+  TNQS_CUDA(cudaMemcpyAsync(out, msg_[de], (size_t)n * n * esz_, cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+}
+void Engine::delete_messages() {
+  TNQS_CUDA(cudaSetDevice(device_));
+  for (int de = 0; de < 2 * ne_; ++de) {
+    if (msg_[de]) { dfree(msg_[de]); msg_[de] = nullptr; }
+    msg_dim_[de] = 0; msg_set_[de] = 0;
+  }
+}
+void Engine::get_bond_dims(int32_t* out) const {
+  for (int e = 0; e < ne_; ++e) out[e] = bond_[e];
+}
+void Engine::set_edge_sequence(const int32_t* seq, int n) {
+  std::vector<int> s(seq, seq + 2 * n);
+  for (int i = 0; i < n; ++i) (void)dedge(s[2 * i], s[2 * i + 1]);
+  seq_ = s;
+}
+void Engine::get_stats(tnqs_stats* out, int reset) {
+  *out = stats_;
+  if (reset) stats_ = tnqs_stats{};
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch wrappers
+// ------------------------------------------------------------------------------------------------
+struct ProfScope {
+  Engine* e; double* acc; bool on; cudaStream_t s; cudaEvent_t a, b;
+  ProfScope(Engine* e_, bool on_, cudaStream_t s_, cudaEvent_t a_, cudaEvent_t b_, double* acc_)
+      : e(e_), acc(acc_), on(on_), s(s_), a(a_), b(b_) { if (on) cudaEventRecord(a, s); }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); *acc += ms; }
+  }
+};
+
+ModeTask Engine::mode_task(int v, int pos, const void* in, void* out, const void* mat) const {
+  ModeTask t{};
+  t.in = in; t.out = out; t.mat = mat;
+  int chi;
+  leg_view(v, pos, &t.outer, &chi, &t.inner);
+  t.ips = t.ops = 0;
+  t.chi_in = t.chi_out = chi;
+  t.KK = t.MM = chi;
+  t.CC = t.outer * t.inner;
+  return t;
+}
+
+GramTask Engine::gram_task(int v, int pos, int planes, const void* X, const void* Y) const {
+  GramTask t{};
+  t.X = X; t.Y = Y;
+  leg_view(v, pos, &t.outer, &t.chi, &t.inner);
+  if (planes > 1) {  // physical index kept open: planes are not folded into `outer`
+    t.outer /= (unsigned)phys_[v];
+    t.xps = t.yps = (long long)t.outer * t.chi * t.inner;
+  }
+  t.MM = planes * t.chi;
+  t.CC = t.outer * t.inner;
+  return t;
+}
+
+template <typename R, bool I1>
+static void launch_mode_variant(const ModeTask* d, int ntasks, int maxtiles, bool small, cudaStream_t s) {
+  for (int off = 0; off < ntasks; off += 65535) {
+    const int nb = std::min(65535, ntasks - off);
+    dim3 grid(maxtiles, nb);
+    if (small) mode_product_kernel<R, I1, 32, 128><<<grid, 256, 0, s>>>(d + off);
+    else mode_product_kernel<R, I1, 64, 64><<<grid, 256, 0, s>>>(d + off);
+  }
+}
+
+void Engine::launch_mode(std::vector<ModeTask>& tasks) {
+  if (tasks.empty()) return;
+  ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.mode_ms);
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool inner1 = pass == 1;
+    std::vector<ModeTask> grp;
+    int maxMM = 0;
+    for (auto& t : tasks) if ((t.inner == 1) == inner1) { grp.push_back(t); maxMM = std::max(maxMM, t.MM); }
+    if (grp.empty()) continue;
+    const bool small = maxMM <= 32;
+    const int tm = small ? 32 : 64, tc = small ? 128 : 64;
+    int maxtiles = 0;
+    for (auto& t : grp) {
+      t.tiles_m = (t.MM + tm - 1) / tm;
+      t.tiles_c = (int)((t.CC + tc - 1) / tc);
+      maxtiles = std::max(maxtiles, t.tiles_m * t.tiles_c);
+    }
+    ModeTask* d = upload(grp);
+    if (c64()) {
+      if (inner1) launch_mode_variant<float, true>(d, (int)grp.size(), maxtiles, small, stream_);
+      else launch_mode_variant<float, false>(d, (int)grp.size(), maxtiles, small, stream_);
+    } else {
+      if (inner1) launch_mode_variant<double, true>(d, (int)grp.size(), maxtiles, small, stream_);
+      else launch_mode_variant<double, false>(d, (int)grp.size(), maxtiles, small, stream_);
+    }
+    count_launch(((int)grp.size() + 65534) / 65535);
+    stats_.mode_launches += ((int)grp.size() + 65534) / 65535;
+    for (auto& t : grp) stats_.mode_flops += 8.0 * t.KK * t.MM * (double)t.CC;
+    TNQS_CUDA(cudaGetLastError());
+  }
+}
+
+template <typename R, typename A, bool I1>
+static void launch_gram_variant(const GramTask* d, int ntasks, int maxsplit, int maxtiles2, bool small,
+                                cudaStream_t s) {
+  for (int off = 0; off < ntasks; off += 65535) {
+    const int nb = std::min(65535, ntasks - off);
+    dim3 grid(maxsplit, maxtiles2, nb);
+    if (small) gram_kernel<R, A, I1, 32><<<grid, 64, 0, s>>>(d + off);
+    else gram_kernel<R, A, I1, 64><<<grid, 256, 0, s>>>(d + off);
+  }
+}
+
+// outs[i] receives the MM×MM result of task i (row-major [i][j], or transposed)
+void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vector<double2*>& outs,
+                         bool transpose) {
+  if (tasks.empty()) return;
+  ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.gram_ms);
+  std::vector<ReduceTask> red(tasks.size());
+  for (int pass = 0; pass < 2; ++pass) {
+    const bool inner1 = pass == 1;
+    std::vector<GramTask> grp;
+    std::vector<int> ids;
+    int maxMM = 0;
+    for (size_t i = 0; i < tasks.size(); ++i)
+      if ((tasks[i].inner == 1) == inner1) { grp.push_back(tasks[i]); ids.push_back((int)i); maxMM = std::max(maxMM, tasks[i].MM); }
+    if (grp.empty()) continue;
+    const bool small = maxMM <= 32;
+    const int ti = small ? 32 : 64;
+    int maxsplit = 1, maxtiles2 = 1;
+    long long ctas_unsplit = 0;
+    for (auto& t : grp) { t.tiles = (t.MM + ti - 1) / ti; ctas_unsplit += (long long)t.tiles * t.tiles; }
+    const long long target = 148ll * 8;
+    for (size_t k = 0; k < grp.size(); ++k) {
+      GramTask& t = grp[k];
+      long long want = (target + ctas_unsplit - 1) / ctas_unsplit;        // splits wanted per task
+      const long long cap = std::max<long long>(1, t.CC / 256);           // ≥256 columns per split
+      long long ns = std::max<long long>(1, std::min(want, cap));
+      ns = std::min<long long>(ns, 1024);
+      unsigned cps = (unsigned)((t.CC + ns - 1) / ns);
+      cps = (cps + TK - 1) / TK * TK;
+      t.cols_per_split = cps;
+      t.nsplit = (int)((t.CC + cps - 1) / cps);
+      t.partial = (double2*)talloc((size_t)t.nsplit * t.MM * t.MM * sizeof(double2));
+      maxsplit = std::max(maxsplit, t.nsplit);
+      maxtiles2 = std::max(maxtiles2, t.tiles * t.tiles);
+      ReduceTask& r = red[ids[k]];
+      r.partial = t.partial; r.out = outs[ids[k]]; r.nsplit = t.nsplit; r.MM = t.MM; r.transpose = transpose ? 1 : 0;
+    }
+    GramTask* d = upload(grp);
+    const int n = (int)grp.size();
+    if (c64()) {
+      if (acc_double) {
+        if (inner1) launch_gram_variant<float, double, true>(d, n, maxsplit, maxtiles2, small, stream_);
+        else launch_gram_variant<float, double, false>(d, n, maxsplit, maxtiles2, small, stream_);
+      } else {
+        if (inner1) launch_gram_variant<float, float, true>(d, n, maxsplit, maxtiles2, small, stream_);
+        else launch_gram_variant<float, float, false>(d, n, maxsplit, maxtiles2, small, stream_);
+      }
+    } else {
+      if (inner1) launch_gram_variant<double, double, true>(d, n, maxsplit, maxtiles2, small, stream_);
+      else launch_gram_variant<double, double, false>(d, n, maxsplit, maxtiles2, small, stream_);
+    }
+    count_launch((n + 65534) / 65535);
+    stats_.gram_launches += (n + 65534) / 65535;
+    for (auto& t : grp) stats_.gram_flops += 8.0 * t.MM * t.MM * (double)t.CC;
+    TNQS_CUDA(cudaGetLastError());
+  }
+  ReduceTask* dr = upload(red);
+  int maxMM = 0;
+  for (auto& r : red) maxMM = std::max(maxMM, r.MM);
+  const int nb = std::max(1, std::min(64, (maxMM * maxMM + 255) / 256));
+  for (int off = 0; off < (int)red.size(); off += 65535) {
+    const int cnt = std::min(65535, (int)red.size() - off);
+    gram_reduce_kernel<<<dim3(nb, cnt), 256, 0, stream_>>>(dr + off);
+    count_launch();
+  }
+  TNQS_CUDA(cudaGetLastError());
+}
+
+void Engine::launch_jacobi(std::vector<JacobiTask>& tasks) {
+  if (tasks.empty()) return;
+  ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.small_ms);
+  int maxn = 0;
+  for (auto& t : tasks) maxn = std::max(maxn, t.n);
+  const int pairs = (maxn + 1) / 2;
+  const int warps = std::max(1, std::min(32, pairs));
+  JacobiTask* d = upload(tasks);
+  jacobi_kernel<<<(unsigned)tasks.size(), warps * 32, 0, stream_>>>(d, 60, 1e-15);
+  count_launch();
+  TNQS_CUDA(cudaGetLastError());
+}
+
+// Run every chain: round r applies step r of every chain that has one; ping-pong scratch buffers.
+void Engine::run_chains(std::vector<Chain>& chains) {
+  size_t maxsteps = 0;
+  std::vector<void*> bufA(chains.size(), nullptr), bufB(chains.size(), nullptr);
+  for (size_t i = 0; i < chains.size(); ++i) {
+    Chain& c = chains[i];
+    maxsteps = std::max(maxsteps, c.steps.size());
+    c.result = site_[c.v];
+    if (c.steps.empty()) continue;
+    const size_t b = (size_t)site_elems(c.v) * esz_;
+    bufA[i] = talloc(b);
+    if (c.steps.size() > 1) bufB[i] = talloc(b);
+  }
+  for (size_t r = 0; r < maxsteps; ++r) {
+    std::vector<ModeTask> tasks;
+    for (size_t i = 0; i < chains.size(); ++i) {
+      Chain& c = chains[i];
+      if (c.steps.size() <= r) continue;
+      const void* in = r == 0 ? site_[c.v] : ((r - 1) % 2 == 0 ? bufA[i] : bufB[i]);
+      void* out = (r % 2 == 0) ? bufA[i] : bufB[i];
+      tasks.push_back(mode_task(c.v, c.steps[r].first, in, out, c.steps[r].second));
+      c.result = out;
+    }
+    launch_mode(tasks);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// belief propagation
+// ------------------------------------------------------------------------------------------------
+
+// Group the sequential edge schedule into dependency levels that reproduce Gauss–Seidel semantics:
+// an update must come after earlier updates of the messages it reads (RAW), not before earlier
+// readers of the message it writes (WAR; same level is fine because a level commits at its end).
+std::vector<std::vector<int>> Engine::bp_levels(const std::vector<int>& seq) const {
+  const int n = (int)seq.size() / 2;
+  std::vector<int> lw(2 * ne_, -1), lr(2 * ne_, -1), lev(n, 0);
+  int nlev = 0;
+  for (int i = 0; i < n; ++i) {
+    const int u = seq[2 * i], v = seq[2 * i + 1];
+    const int w = dedge(u, v);
+    int L = 0;
+    for (auto& l : inc_[u]) {
+      if (l.nbr == v) continue;
+      const int r = dedge(l.nbr, u);
+      if (lw[r] >= 0) L = std::max(L, lw[r] + 1);
+    }
+    L = std::max(L, lr[w]);
+    if (lw[w] >= 0) L = std::max(L, lw[w] + 1);
+    lev[i] = L;
+    lw[w] = L;
+    for (auto& l : inc_[u]) {
+      if (l.nbr == v) continue;
+      const int r = dedge(l.nbr, u);
+      lr[r] = std::max(lr[r], L);
+    }
+    nlev = std::max(nlev, L + 1);
+  }
+  std::vector<std::vector<int>> out(nlev);
+  for (int i = 0; i < n; ++i) out[lev[i]].push_back(i);
+  return out;
+}
+
+// one level: every item i is the update of message seq[i] (abstractbeliefpropagationcache.jl:162-190)
+void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& items, double* d_diff) {
+  const size_t budget = scratch_budget();
+  size_t pos = 0;
+  while (pos < items.size()) {
+    // chunk by scratch
+    size_t end = pos, bytes = 0;
+    while (end < items.size()) {
+      const int u = seq[2 * items[end]];
+      const size_t need = (inc_[u].size() > 1 ? 2 : 0) * (size_t)site_elems(u) * esz_;
+      if (end > pos && bytes + need > budget) break;
+      bytes += need;
+      ++end;
+    }
+    const int n = (int)(end - pos);
+    std::vector<Chain> chains(n);
+    for (int k = 0; k < n; ++k) {
+      const int it = items[pos + k];
+      const int u = seq[2 * it], v = seq[2 * it + 1];
+      chains[k].v = u;
+      for (size_t p = 0; p < inc_[u].size(); ++p) {
+        const int w = inc_[u][p].nbr;
+        if (w == v) continue;
+        const int de = dedge(w, u);
+        if (!msg_set_[de]) continue;  // identity default: nothing to absorb
+        chains[k].steps.push_back({(int)p, msg_[de]});
+      }
+    }
+    run_chains(chains);
+    std::vector<GramTask> gt(n);
+    std::vector<double2*> outs(n);
+    std::vector<BpFinTask> fin(n);
+    for (int k = 0; k < n; ++k) {
+      const int it = items[pos + k];
+      const int u = seq[2 * it], v = seq[2 * it + 1];
+      const int de = dedge(u, v);
+      const int e = de / 2;
+      gt[k] = gram_task(u, leg_pos(u, e), 1, site_[u], chains[k].result);
+      const int chi = bond_[e];
+      outs[k] = (double2*)talloc((size_t)chi * chi * sizeof(double2));
+      if (!msg_next_[de] || msg_next_dim_[de] != chi) {
+        if (msg_next_[de]) dfree(msg_next_[de]);
+        msg_next_[de] = dalloc((size_t)chi * chi * esz_);
+        msg_next_dim_[de] = chi;
+      }
+      fin[k].g = outs[k]; fin[k].old_msg = msg_[de]; fin[k].new_msg = msg_next_[de];
+      fin[k].diff = d_diff + it; fin[k].chi = chi;
+    }
+    launch_gram(gt, /*acc_double=*/false, outs, /*transpose=*/true);
+    {
+      BpFinTask* df = upload(fin);
+      if (c64()) bp_finalize_kernel<float><<<n, 256, 0, stream_>>>(df);
+      else bp_finalize_kernel<double><<<n, 256, 0, stream_>>>(df);
+      count_launch();
+      TNQS_CUDA(cudaGetLastError());
+    }
+    free_temps();
+    pos = end;
+  }
+  for (int it : items) {  // commit the level
+    const int de = dedge(seq[2 * it], seq[2 * it + 1]);
+    std::swap(msg_[de], msg_next_[de]);
+    std::swap(msg_dim_[de], msg_next_dim_[de]);
+    msg_set_[de] = 1;
+  }
+  stats_.bp_messages += (int64_t)items.size();
+}
+
+tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  std::vector<int> seq;
+  if (o && o->edge_sequence && o->n_seq > 0) seq.assign(o->edge_sequence, o->edge_sequence + 2 * o->n_seq);
+  else seq = seq_;
+  if (seq.empty() && ne_ > 0)
+    throw Error(TNQS_EINVAL, "no BP edge sequence: call tnqs_set_edge_sequence or pass one in tnqs_bp_opts");
+  const int nseq = (int)seq.size() / 2;
+  // defaults (beliefpropagationcache.jl:103-119)
+  int maxiter = is_tree_ ? 1 : 25;
+  bool use_tol = !is_tree_;
+  double tol = c64() ? 1e-5 : 1e-8;
+  if (o) {
+    if (o->maxiter > 0) maxiter = o->maxiter;
+    use_tol = o->use_tolerance != 0;
+    if (o->tolerance >= 0) tol = o->tolerance;
+  }
+  tnqs_bp_report rep{maxiter, use_tol ? 0 : 1, 0.0};
+  if (nseq == 0) { rep.niter = 0; rep.converged = 1; return rep; }
+  cudaEvent_t t0, t1;
+  TNQS_CUDA(cudaEventCreate(&t0));
+  TNQS_CUDA(cudaEventCreate(&t1));
+  TNQS_CUDA(cudaEventRecord(t0, stream_));
+  for (int de = 0; de < 2 * ne_; ++de) materialize_message(de);
+  free_temps();
+  const auto levels = bp_levels(seq);
+  double* d_diff = (double*)dalloc(sizeof(double) * nseq);
+  std::vector<double> h_diff(nseq);
+  for (int it = 1; it <= maxiter; ++it) {
+    for (auto& lv : levels) bp_level(seq, lv, d_diff);
+    stats_.bp_sweeps += 1;
+    if (use_tol) {
+      TNQS_CUDA(cudaMemcpyAsync(h_diff.data(), d_diff, sizeof(double) * nseq, cudaMemcpyDeviceToHost, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));
+      double s = 0;
+      for (double x : h_diff) s += x;
+      rep.diff = s / nseq;
+      if (rep.diff <= tol) { rep.converged = 1; rep.niter = it; break; }
+    }
+  }
+  dfree(d_diff);
+  TNQS_CUDA(cudaEventRecord(t1, stream_));
+  TNQS_CUDA(cudaEventSynchronize(t1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  stats_.bp_ms += ms;
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  return rep;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate application
+// ------------------------------------------------------------------------------------------------
+void Engine::normalize_sites(const std::vector<int>& vs) {
+  if (vs.empty()) return;
+  std::vector<NormTask> t(vs.size());
+  for (size_t i = 0; i < vs.size(); ++i) {
+    t[i].data = site_[vs[i]];
+    t[i].n = site_elems(vs[i]);
+    t[i].partial = (double*)talloc(sizeof(double) * NORM_BLOCKS);
+  }
+  NormTask* d = upload(t);
+  long long maxn = 0;
+  for (auto& x : t) maxn = std::max(maxn, x.n);
+  const int nb = (int)std::max<long long>(1, std::min<long long>(512, (maxn + 1023) / 1024));
+  for (int off = 0; off < (int)t.size(); off += 65535) {
+    const int cnt = std::min(65535, (int)t.size() - off);
+    if (c64()) {
+      sumsq_kernel<float><<<dim3(NORM_BLOCKS, cnt), 256, 0, stream_>>>(d + off);
+      scale_kernel<float><<<dim3(nb, cnt), 256, 0, stream_>>>(d + off);
+    } else {
+      sumsq_kernel<double><<<dim3(NORM_BLOCKS, cnt), 256, 0, stream_>>>(d + off);
+      scale_kernel<double><<<dim3(nb, cnt), 256, 0, stream_>>>(d + off);
+    }
+    count_launch(2);
+  }
+  TNQS_CUDA(cudaGetLastError());
+}
+
+void Engine::apply_one_site_batch(const std::vector<std::pair<int, std::vector<cplx>>>& g, bool normalize) {
+  if (g.empty()) return;
+  std::vector<OneSiteTask> t(g.size());
+  std::vector<int> vs;
+  long long maxplane = 0;
+  for (size_t i = 0; i < g.size(); ++i) {
+    const int v = g[i].first;
+    const int d = phys_[v];
+    t[i].data = site_[v];
+    t[i].plane = site_elems(v) / d;
+    t[i].d = d;
+    for (int k = 0; k < d * d; ++k) { t[i].U[k].x = g[i].second[k].real(); t[i].U[k].y = g[i].second[k].imag(); }
+    maxplane = std::max(maxplane, t[i].plane);
+    vs.push_back(v);
+  }
+  OneSiteTask* dt = upload(t);
+  const int nb = (int)std::max<long long>(1, std::min<long long>(512, (maxplane + 255) / 256));
+  for (int off = 0; off < (int)t.size(); off += 65535) {
+    const int cnt = std::min(65535, (int)t.size() - off);
+    if (c64()) onesite_kernel<float><<<dim3(nb, cnt), 256, 0, stream_>>>(dt + off);
+    else onesite_kernel<double><<<dim3(nb, cnt), 256, 0, stream_>>>(dt + off);
+    count_launch();
+  }
+  TNQS_CUDA(cudaGetLastError());
+  if (normalize) normalize_sites(vs);
+  free_temps();
+}
+
+// One batch of vertex-disjoint two-site gates: the whole of simple_update's two-site branch
+// (simple_update.jl:29-68) plus apply_gate!'s write-back (apply_gates.jl:126-140), batched.
+void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_t* verts,
+                                  const double* mats, const std::vector<size_t>& mat_off,
+                                  const tnqs_apply_opts& ao, double* errs) {
+  if (gate_ids.empty()) return;
+  const double eps = c64() ? 1.1920928955078125e-07 : 2.220446049250313e-16;
+  const double sqrt_cutoff = ao.sqrt_cutoff >= 0 ? ao.sqrt_cutoff : 10 * eps;  // simple_update.jl:32-33
+  const bool normalize = ao.normalize_tensors != 0;
+  const size_t budget = scratch_budget();
+  size_t gpos = 0;
+  while (gpos < gate_ids.size()) {
+    size_t gend = gpos, bytes = 0;
+    while (gend < gate_ids.size()) {
+      const int g = gate_ids[gend];
+      const size_t need = 3 * ((size_t)site_elems(verts[2 * g]) + (size_t)site_elems(verts[2 * g + 1])) * esz_;
+      if (gend > gpos && bytes + need > budget) break;
+      bytes += need;
+      ++gend;
+    }
+    const int ng = (int)(gend - gpos);
+
+    // ---- 1. environments: eigendecompose every non-default incoming message --------------------
+    struct EnvRef { int gate, site, pos, de, task; };
+    std::vector<EnvRef> envs;
+    std::vector<MsgEigTask> mt;
+    for (int k = 0; k < ng; ++k) {
+      const int g = gate_ids[gpos + k];
+      for (int s = 0; s < 2; ++s) {
+        const int v = verts[2 * g + s], o = verts[2 * g + 1 - s];
+        for (size_t p = 0; p < inc_[v].size(); ++p) {
+          const int w = inc_[v][p].nbr;
+          if (w == o) continue;
+          const int de = dedge(w, v);
+          if (!msg_set_[de]) continue;  // identity default ⇒ √M = M^{-1/2} = 1
+          const int chi = bond_[de / 2];
+          MsgEigTask t{};
+          t.M = msg_[de];
+          t.A = (double2*)talloc((size_t)chi * chi * sizeof(double2));
+          t.V = (double2*)talloc((size_t)chi * chi * sizeof(double2));
+          t.sqrtM = talloc((size_t)chi * chi * esz_);
+          t.proj = talloc((size_t)chi * chi * esz_);
+          t.chi = chi;
+          t.flags = nullptr;
+          t.lam = (double*)talloc(sizeof(double) * chi);
+          envs.push_back({k, s, (int)p, de, (int)mt.size()});
+          mt.push_back(t);
+        }
+      }
+    }
+    int* d_flags = (int*)talloc(sizeof(int) * 2 * std::max<size_t>(1, mt.size()));
+    for (size_t i = 0; i < mt.size(); ++i) mt[i].flags = d_flags + 2 * i;
+    if (!mt.empty()) {
+      MsgEigTask* dm = upload(mt);
+      if (c64()) msg_prepare_kernel<float><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm);
+      else msg_prepare_kernel<double><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm);
+      count_launch();
+      std::vector<JacobiTask> jt(mt.size());
+      std::vector<double*> sv(mt.size());
+      for (size_t i = 0; i < mt.size(); ++i) {
+        jt[i].A = mt[i].A; jt[i].V = mt[i].V; jt[i].m = jt[i].n = mt[i].chi;
+        jt[i].sval = (double*)talloc(sizeof(double) * mt[i].chi);
+        jt[i].perm = (int*)talloc(sizeof(int) * mt[i].chi);
+      }
+      launch_jacobi(jt);
+      if (c64()) msg_finish_kernel<float><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm, sqrt_cutoff);
+      else msg_finish_kernel<double><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm, sqrt_cutoff);
+      count_launch();
+      TNQS_CUDA(cudaGetLastError());
+    }
+
+    // ---- 2. gauge: T̃ = T ×_ext √M (simple_update.jl:43-44) -------------------------------------
+    std::vector<Chain> gauge(2 * ng);
+    for (int k = 0; k < ng; ++k)
+      for (int s = 0; s < 2; ++s) gauge[2 * k + s].v = verts[2 * gate_ids[gpos + k] + s];
+    for (auto& en : envs) gauge[2 * en.gate + en.site].steps.push_back({en.pos, mt[en.task].sqrtM});
+    run_chains(gauge);
+
+    // ---- 3. Gram of the gauged tensor over its external legs (R†R of the QR at :47-48) ---------
+    std::vector<GramTask> gt(2 * ng);
+    std::vector<double2*> G(2 * ng);
+    std::vector<int> nn(2 * ng), epos(2 * ng);
+    std::vector<int> ebond(ng);
+    for (int k = 0; k < ng; ++k) {
+      const int g = gate_ids[gpos + k];
+      const int a = verts[2 * g], b = verts[2 * g + 1];
+      const int e = dedge(a, b) / 2;
+      ebond[k] = e;
+      for (int s = 0; s < 2; ++s) {
+        const int v = s == 0 ? a : b;
+        epos[2 * k + s] = leg_pos(v, e);
+        gt[2 * k + s] = gram_task(v, epos[2 * k + s], phys_[v], gauge[2 * k + s].result, gauge[2 * k + s].result);
+        nn[2 * k + s] = gt[2 * k + s].MM;
+        G[2 * k + s] = (double2*)talloc((size_t)nn[2 * k + s] * nn[2 * k + s] * sizeof(double2));
+      }
+    }
+    launch_gram(gt, /*acc_double=*/true, G, /*transpose=*/false);
+
+    // ---- 4. eig(G), θ, SVD(θ), truncation ------------------------------------------------------
+    std::vector<SuGateTask> st(ng);
+    int* d_keep = (int*)talloc(sizeof(int) * ng);
+    double* d_err = (double*)talloc(sizeof(double) * ng);
+    double* d_ss = (double*)talloc(sizeof(double) * ng);
+    std::vector<int> keep_cap(ng);
+    {
+      std::vector<HermTask> ht(2 * ng);
+      std::vector<JacobiTask> jg(2 * ng);
+      for (int i = 0; i < 2 * ng; ++i) {
+        const int n = nn[i];
+        ht[i].G = G[i]; ht[i].n = n;
+        ht[i].A = (double2*)talloc((size_t)n * n * sizeof(double2));
+        ht[i].V = (double2*)talloc((size_t)n * n * sizeof(double2));
+        jg[i].A = ht[i].A; jg[i].V = ht[i].V; jg[i].m = jg[i].n = n;
+        jg[i].sval = (double*)talloc(sizeof(double) * n);
+        jg[i].perm = (int*)talloc(sizeof(int) * n);
+      }
+      HermTask* dh = upload(ht);
+      herm_prepare_kernel<<<2 * ng, 256, 0, stream_>>>(dh);
+      count_launch();
+      launch_jacobi(jg);
+      std::vector<JacobiTask> jt(ng);
+      for (int k = 0; k < ng; ++k) {
+        const int g = gate_ids[gpos + k];
+        SuGateTask& t = st[k];
+        std::memset(&t, 0, sizeof(t));
+        const int d0 = phys_[verts[2 * g]], d1 = phys_[verts[2 * g + 1]];
+        const int chi = bond_[ebond[k]];
+        t.d[0] = d0; t.d[1] = d1; t.chi_b = chi;
+        for (int s = 0; s < 2; ++s) {
+          t.GA[s] = ht[2 * k + s].A; t.GV[s] = ht[2 * k + s].V;
+          t.sq[s] = (double*)talloc(sizeof(double) * nn[2 * k + s]);
+          t.isq[s] = (double*)talloc(sizeof(double) * nn[2 * k + s]);
+        }
+        const int D = d0 * d1;
+        const double* gm = mats + mat_off[g];
+        for (int i = 0; i < D * D; ++i) { t.gate[i].x = gm[2 * i]; t.gate[i].y = gm[2 * i + 1]; }
+        const int rows = nn[2 * k] * d0, cols = nn[2 * k + 1] * d1;
+        t.theta = (double2*)talloc((size_t)rows * cols * sizeof(double2));
+        t.theta0 = (double2*)talloc((size_t)rows * cols * sizeof(double2));
+        double* sval = (double*)talloc(sizeof(double) * cols);
+        int* perm = (int*)talloc(sizeof(int) * cols);
+        t.sval = sval; t.perm = perm;
+        t.sigma = (double*)talloc(sizeof(double) * cols);
+        t.keep = d_keep + k; t.err = d_err + k; t.sumsq_kept = d_ss + k;
+        // thin QR of the reference: r_s = min(∏ external dims, d_s·χ_b)  (simple_update.jl:47-48)
+        long long full = 1ll << 40;
+        for (int s = 0; s < 2; ++s) {
+          const int v = verts[2 * g + s];
+          const long long ext = site_elems(v) / ((long long)phys_[v] * chi);
+          full = std::min(full, std::min<long long>(ext, nn[2 * k + s]) * phys_[v]);
+        }
+        t.full = (int)full;
+        int cap = (int)full;
+        if (ao.maxdim > 0) cap = std::min(cap, std::max(ao.maxdim, std::max(1, ao.mindim)));
+        keep_cap[k] = cap;
+        t.Rp = (double2*)talloc((size_t)cols * cap * sizeof(double2));
+        t.X[0] = talloc((size_t)nn[2 * k] * d0 * cap * esz_);
+        t.X[1] = talloc((size_t)nn[2 * k + 1] * d1 * cap * esz_);
+        jt[k].A = t.theta; jt[k].V = nullptr; jt[k].m = rows; jt[k].n = cols; jt[k].sval = sval; jt[k].perm = perm;
+      }
+      SuGateTask* ds = upload(st);
+      su_theta_kernel<<<ng, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
+      count_launch();
+      launch_jacobi(jt);
+      su_truncate_kernel<<<(ng + 63) / 64, 64, 0, stream_>>>(ds, ng, ao.maxdim, ao.mindim, ao.cutoff);
+      count_launch();
+      TNQS_CUDA(cudaGetLastError());
+      // the host needs the kept ranks to size the new tensors: the one sync of the batch
+      std::vector<int> keep(ng), flags(2 * std::max<size_t>(1, mt.size()));
+      std::vector<double> err(ng);
+      TNQS_CUDA(cudaMemcpyAsync(keep.data(), d_keep, sizeof(int) * ng, cudaMemcpyDeviceToHost, stream_));
+      TNQS_CUDA(cudaMemcpyAsync(err.data(), d_err, sizeof(double) * ng, cudaMemcpyDeviceToHost, stream_));
+      if (!mt.empty())
+        TNQS_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * 2 * mt.size(), cudaMemcpyDeviceToHost, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));
+      for (size_t i = 0; i < mt.size(); ++i)
+        if (flags[2 * i + 1]) {
+          free_temps();
+          throw Error(TNQS_EDOMAIN, "DomainError: sqrt of a negative message eigenvalue (message into vertex " +
+                                        std::to_string(verts[2 * gate_ids[gpos + envs[i].gate] + envs[i].site]) + ")");
+        }
+      if (c64()) su_factors_kernel<float><<<ng, 256, 0, stream_>>>(ds);
+      else su_factors_kernel<double><<<ng, 256, 0, stream_>>>(ds);
+      count_launch();
+      TNQS_CUDA(cudaGetLastError());
+
+      // ---- 5. un-gauge with the projector and contract with the new factor (:62-64) -----------
+      std::vector<Chain> proj(2 * ng);
+      for (int k = 0; k < ng; ++k)
+        for (int s = 0; s < 2; ++s) proj[2 * k + s].v = verts[2 * gate_ids[gpos + k] + s];
+      for (auto& en : envs)
+        if (!flags[2 * en.task]) proj[2 * en.gate + en.site].steps.push_back({en.pos, mt[en.task].proj});
+      run_chains(proj);
+      std::vector<ModeTask> fin(2 * ng);
+      std::vector<void*> newbuf(2 * ng);
+      for (int k = 0; k < ng; ++k) {
+        const int g = gate_ids[gpos + k];
+        for (int s = 0; s < 2; ++s) {
+          const int v = verts[2 * g + s];
+          const int d = phys_[v];
+          const int pos = epos[2 * k + s];
+          ModeTask& t = fin[2 * k + s];
+          t = ModeTask{};
+          int chi;
+          leg_view(v, pos, &t.outer, &chi, &t.inner);
+          t.outer /= (unsigned)d;
+          t.chi_in = chi; t.chi_out = keep[k];
+          t.KK = d * chi; t.MM = d * keep[k];
+          t.CC = t.outer * t.inner;
+          t.ips = (long long)t.outer * chi * t.inner;
+          t.ops = (long long)t.outer * keep[k] * t.inner;
+          t.in = proj[2 * k + s].result;
+          newbuf[2 * k + s] = dalloc((size_t)t.ops * d * esz_);
+          t.out = newbuf[2 * k + s];
+          t.mat = st[k].X[s];
+        }
+      }
+      launch_mode(fin);
+      // ---- 6. commit: tensors, bond dimension, messages (apply_gates.jl:126-140) ----------------
+      std::vector<int> touched;
+      std::vector<DiagTask> dt;
+      for (int k = 0; k < ng; ++k) {
+        const int g = gate_ids[gpos + k];
+        const int e = ebond[k];
+        bond_[e] = keep[k];
+        for (int s = 0; s < 2; ++s) {
+          const int v = verts[2 * g + s];
+          dfree(site_[v]);
+          site_[v] = newbuf[2 * k + s];
+          sshape_[v][epos[2 * k + s]] = keep[k];
+          touched.push_back(v);
+        }
+        for (int de = 2 * e; de < 2 * e + 2; ++de) {
+          if (msg_[de]) dfree(msg_[de]);
+          msg_[de] = dalloc((size_t)keep[k] * keep[k] * esz_);
+          msg_dim_[de] = keep[k];
+          msg_set_[de] = 1;
+          DiagTask d{};
+          d.out = msg_[de]; d.chi = keep[k]; d.diag = st[k].sigma;
+          d.scale_sumsq = normalize ? d_ss + k : nullptr;
+          dt.push_back(d);
+        }
+        errs[g] = err[k];
+      }
+      if (normalize) normalize_sites(touched);
+      DiagTask* dd = upload(dt);
+      int maxchi = 1;
+      for (auto& d : dt) maxchi = std::max(maxchi, d.chi);
+      const int nb = std::max(1, std::min(64, (maxchi * maxchi + 255) / 256));
+      if (c64()) diag_fill_kernel<float><<<dim3(nb, (unsigned)dt.size()), 256, 0, stream_>>>(dd);
+      else diag_fill_kernel<double><<<dim3(nb, (unsigned)dt.size()), 256, 0, stream_>>>(dd);
+      count_launch();
+      TNQS_CUDA(cudaGetLastError());
+    }
+    stats_.two_site_gates += ng;
+    free_temps();
+    gpos = gend;
+  }
+}
+
+void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts, const double* mats,
+                         const tnqs_apply_opts* aop, const tnqs_bp_opts* bo, int update_cache,
+                         double* errs, tnqs_bp_report* reports, int max_reports, int* n_reports) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  tnqs_apply_opts ao{0, 1, -1.0, 1, -1.0};
+  if (aop) ao = *aop;
+  if (ao.mindim < 1) ao.mindim = 1;
+  // validate everything before touching the state (apply_gates.jl:109-120)
+  std::vector<size_t> mat_off(ngates);
+  size_t off = 0;
+  for (int i = 0; i < ngates; ++i) {
+    if (nverts[i] < 1 || nverts[i] > 2)
+      throw Error(TNQS_ENSITES, "apply_gate!: only one- and two-site gates are supported; received a gate acting on " +
+                                    std::to_string(nverts[i]) + " vertices.");
+    const int a = verts[2 * i];
+    if (a < 0 || a >= nv_) throw Error(TNQS_EINVAL, "gate vertex out of range");
+    int D = phys_[a];
+    if (nverts[i] == 2) {
+      const int b = verts[2 * i + 1];
+      if (b < 0 || b >= nv_) throw Error(TNQS_EINVAL, "gate vertex out of range");
+      bool adj = false;
+      for (auto& l : inc_[a]) adj |= (l.nbr == b);
+      if (!adj)
+        throw Error(TNQS_ENOTADJ, "apply_gate!: cannot apply a two-site gate on the non-adjacent vertices " +
+                                      std::to_string(a) + " and " + std::to_string(b) + ".");
+      D *= phys_[b];
+    }
+    mat_off[i] = off;
+    off += 2 * (size_t)D * D;
+  }
+  int nrep = 0;
+  cudaEvent_t t0, t1;
+  TNQS_CUDA(cudaEventCreate(&t0));
+  TNQS_CUDA(cudaEventCreate(&t1));
+  TNQS_CUDA(cudaEventRecord(t0, stream_));
+  const double bp_before = stats_.bp_ms;
+
+  // Between two BP refreshes, order gates by per-vertex dependency depth; every depth is one batch
+  // of vertex-disjoint two-site gates plus one batch of (fused) one-site gates.
+  std::vector<int> seg;
+  auto flush = [&]() {
+    if (seg.empty()) return;
+    struct Stage { std::vector<int> two; std::vector<std::pair<int, std::vector<cplx>>> one; };
+    std::vector<Stage> stages;
+    std::vector<int> last_stage(nv_, -1), open_one(nv_, -1);  // open_one: index into stage.one
+    for (int g : seg) {
+      if (nverts[g] == 1) {
+        const int v = verts[2 * g], d = phys_[v];
+        std::vector<cplx> U(d * d);
+        for (int k = 0; k < d * d; ++k) U[k] = cplx(mats[mat_off[g] + 2 * k], mats[mat_off[g] + 2 * k + 1]);
+        if (open_one[v] >= 0) {  // fuse with the preceding one-site gate on this vertex
+          auto& prev = stages[last_stage[v]].one[open_one[v]].second;
+          std::vector<cplx> W(d * d);
+          for (int i = 0; i < d; ++i)
+            for (int j = 0; j < d; ++j) {
+              cplx s = 0;
+              for (int k = 0; k < d; ++k) s += U[i * d + k] * prev[k * d + j];
+              W[i * d + j] = s;
+            }
+          prev = W;
+        } else {
+          const int sidx = last_stage[v] + 1;
+          if ((int)stages.size() <= sidx) stages.resize(sidx + 1);
+          stages[sidx].one.push_back({v, U});
+          open_one[v] = (int)stages[sidx].one.size() - 1;
+          last_stage[v] = sidx;
+        }
+      } else {
+        const int a = verts[2 * g], b = verts[2 * g + 1];
+        const int sidx = std::max(last_stage[a], last_stage[b]) + 1;
+        if ((int)stages.size() <= sidx) stages.resize(sidx + 1);
+        stages[sidx].two.push_back(g);
+        last_stage[a] = last_stage[b] = sidx;
+        open_one[a] = open_one[b] = -1;
+      }
+    }
+    for (auto& st : stages) {
+      apply_two_site_batch(st.two, verts, mats, mat_off, ao, errs);
+      apply_one_site_batch(st.one, ao.normalize_tensors != 0);
+    }
+    seg.clear();
+  };
+
+  std::vector<char> affected(nv_, 0);
+  for (int i = 0; i < ngates; ++i) {
+    errs[i] = 0.0;
+    bool need = false;
+    if (nverts[i] >= 2) need = affected[verts[2 * i]] || affected[verts[2 * i + 1]];
+    if (update_cache && need) {  // apply_gates.jl:68-83
+      flush();
+      const tnqs_bp_report r = bp_update(bo);
+      if (reports && nrep < max_reports) reports[nrep] = r;
+      ++nrep;
+      std::fill(affected.begin(), affected.end(), 0);
+    }
+    seg.push_back(i);
+    for (int k = 0; k < nverts[i]; ++k) affected[verts[2 * i + k]] = 1;
+  }
+  flush();
+  if (update_cache) {  // apply_gates.jl:93-95
+    const tnqs_bp_report r = bp_update(bo);
+    if (reports && nrep < max_reports) reports[nrep] = r;
+    ++nrep;
+  }
+  if (n_reports) *n_reports = nrep;
+  TNQS_CUDA(cudaEventRecord(t1, stream_));
+  TNQS_CUDA(cudaEventSynchronize(t1));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, t0, t1);
+  stats_.su_ms += ms - (stats_.bp_ms - bp_before);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// expectation values (expect.jl:59-82)
+// ------------------------------------------------------------------------------------------------
+void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, double* out) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  if (nobs <= 0) return;
+  std::vector<Chain> chains(nobs);
+  for (int i = 0; i < nobs; ++i) {
+    const int v = verts[i];
+    if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "observable vertex out of range");
+    chains[i].v = v;
+    for (size_t p = 0; p < inc_[v].size(); ++p) {
+      const int de = dedge(inc_[v][p].nbr, v);
+      if (!msg_set_[de] || !msg_[de]) continue;
+      chains[i].steps.push_back({(int)p, msg_[de]});
+    }
+  }
+  run_chains(chains);
+  std::vector<GramTask> gt(nobs);
+  std::vector<double2*> outs(nobs);
+  size_t tot = 0;
+  std::vector<size_t> offs(nobs);
+  for (int i = 0; i < nobs; ++i) { offs[i] = tot; tot += (size_t)phys_[verts[i]] * phys_[verts[i]]; }
+  double2* d_rho = (double2*)talloc(tot * sizeof(double2));
+  for (int i = 0; i < nobs; ++i) {
+    gt[i] = gram_task(verts[i], -1, 1, site_[verts[i]], chains[i].result);
+    outs[i] = d_rho + offs[i];
+  }
+  launch_gram(gt, true, outs, /*transpose=*/true);  // buffer[s*d+s'] = ρ[s][s']
+  std::vector<cplx> rho(tot);
+  TNQS_CUDA(cudaMemcpyAsync(rho.data(), d_rho, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+  size_t opoff = 0;
+  for (int i = 0; i < nobs; ++i) {
+    const int d = phys_[verts[i]];
+    const cplx* r = rho.data() + offs[i];
+    cplx num = 0, den = 0;
+    for (int s = 0; s < d; ++s) {
+      den += r[s * d + s];
+      for (int sp = 0; sp < d; ++sp) {
+        const cplx O(ops[opoff + 2 * (sp * d + s)], ops[opoff + 2 * (sp * d + s) + 1]);
+        num += O * r[s * d + sp];
+      }
+    }
+    opoff += 2 * (size_t)d * d;
+    const cplx val = num / den;
+    out[2 * i] = val.real(); out[2 * i + 1] = val.imag();
+  }
+}
+
+void Engine::expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  if (nobs <= 0) return;
+  std::vector<Chain> chains(2 * nobs);
+  std::vector<int> pos(2 * nobs);
+  for (int i = 0; i < nobs; ++i) {
+    const int a = verts[2 * i], b = verts[2 * i + 1];
+    const int e = dedge(a, b) / 2;
+    for (int s = 0; s < 2; ++s) {
+      const int v = s == 0 ? a : b, o = s == 0 ? b : a;
+      chains[2 * i + s].v = v;
+      pos[2 * i + s] = leg_pos(v, e);
+      for (size_t p = 0; p < inc_[v].size(); ++p) {
+        if (inc_[v][p].nbr == o) continue;
+        const int de = dedge(inc_[v][p].nbr, v);
+        if (!msg_set_[de] || !msg_[de]) continue;
+        chains[2 * i + s].steps.push_back({(int)p, msg_[de]});
+      }
+    }
+  }
+  run_chains(chains);
+  std::vector<GramTask> gt(2 * nobs);
+  std::vector<double2*> outs(2 * nobs);
+  std::vector<size_t> offs(2 * nobs);
+  size_t tot = 0;
+  for (int i = 0; i < 2 * nobs; ++i) {
+    const int v = chains[i].v;
+    gt[i] = gram_task(v, pos[i], phys_[v], site_[v], chains[i].result);
+    offs[i] = tot;
+    tot += (size_t)gt[i].MM * gt[i].MM;
+  }
+  double2* d_e = (double2*)talloc(tot * sizeof(double2));
+  for (int i = 0; i < 2 * nobs; ++i) outs[i] = d_e + offs[i];
+  launch_gram(gt, true, outs, /*transpose=*/false);  // buffer[(s'b')*n + (s b)] = E[s,b,s',b']
+  std::vector<cplx> E(tot);
+  TNQS_CUDA(cudaMemcpyAsync(E.data(), d_e, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+  size_t opoff = 0;
+  for (int i = 0; i < nobs; ++i) {
+    const int a = verts[2 * i], b = verts[2 * i + 1];
+    const int d0 = phys_[a], d1 = phys_[b];
+    const int chi = bond_[dedge(a, b) / 2];
+    const int n0 = d0 * chi, n1 = d1 * chi;
+    const cplx* E0 = E.data() + offs[2 * i];
+    const cplx* E1 = E.data() + offs[2 * i + 1];
+    const double* O0 = ops + opoff;
+    const double* O1 = ops + opoff + 2 * (size_t)d0 * d0;
+    opoff += 2 * ((size_t)d0 * d0 + (size_t)d1 * d1);
+    cplx num = 0, den = 0;
+    for (int s0 = 0; s0 < d0; ++s0) for (int t0 = 0; t0 < d0; ++t0)
+      for (int s1 = 0; s1 < d1; ++s1) for (int t1 = 0; t1 < d1; ++t1) {
+        cplx rho = 0;  // ρ[s0,s1,t0,t1] = Σ_{b,c} E0[s0,b,t0,c] E1[s1,b,t1,c]
+        for (int bb = 0; bb < chi; ++bb) for (int cc = 0; cc < chi; ++cc)
+          rho += E0[(size_t)(t0 * chi + cc) * n0 + (s0 * chi + bb)] * E1[(size_t)(t1 * chi + cc) * n1 + (s1 * chi + bb)];
+        const cplx o0(O0[2 * (t0 * d0 + s0)], O0[2 * (t0 * d0 + s0) + 1]);
+        const cplx o1(O1[2 * (t1 * d1 + s1)], O1[2 * (t1 * d1 + s1) + 1]);
+        num += o0 * o1 * rho;
+        if (s0 == t0 && s1 == t1) den += rho;
+      }
+    const cplx val = num / den;
+    out[2 * i] = val.real(); out[2 * i + 1] = val.imag();
+  }
+}
+
+}  // namespace tnqs

@@ -1,0 +1,133 @@
+// engine.cuh — host-side engine: flat device-resident block layout indexed by graph vertex / edge,
+// the BP level scheduler, the batched simple-update pipeline and local expectation values.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/tnqs_b200.h"
+#include "kernels_small.cuh"
+#include "kernels_tensor.cuh"
+
+namespace tnqs {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define TNQS_CUDA(x)                                                                           \
+  do {                                                                                         \
+    cudaError_t e_ = (x);                                                                      \
+    if (e_ != cudaSuccess)                                                                     \
+      throw ::tnqs::Error(TNQS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
+struct Leg {
+  int edge, nbr;
+};
+
+// one chain of mode products on a site tensor: result = T_v ×_{pos_0} M_0 ×_{pos_1} M_1 …
+struct Chain {
+  int v = -1;
+  std::vector<std::pair<int, const void*>> steps;  // (bond-leg position, χ×χ matrix)
+  const void* result = nullptr;                    // filled by run_chains
+};
+
+class Engine {
+ public:
+  Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t* phys, const int32_t* bond,
+         int device);
+  Engine(const Engine& o);  // deep copy (tnqs_clone)
+  ~Engine();
+
+  // import / export
+  void set_site(int v, const void* data, int ndim, const int64_t* shape);
+  void site_shape(int v, int* ndim, int64_t* shape) const;
+  void get_site(int v, void* data, int64_t cap);
+  void set_message(int src, int dst, const void* data, int chi);
+  void get_message(int src, int dst, void* out, int64_t cap, int* chi, int* is_set);
+  void delete_messages();
+  void get_bond_dims(int32_t* out) const;
+  void set_edge_sequence(const int32_t* seq, int n);
+
+  // hot path
+  void apply_gates(int ngates, const int32_t* nverts, const int32_t* verts, const double* mats,
+                   const tnqs_apply_opts* ao, const tnqs_bp_opts* bo, int update_cache, double* errs,
+                   tnqs_bp_report* reports, int max_reports, int* n_reports);
+  tnqs_bp_report bp_update(const tnqs_bp_opts* opts);
+  void expect_local(int nobs, const int32_t* verts, const double* ops, double* out);
+  void expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out);
+
+  void get_stats(tnqs_stats* out, int reset);
+  void set_profiling(int on) { profiling_ = on != 0; }
+
+  int dtype() const { return dtype_; }
+
+ private:
+  // ---- static description -------------------------------------------------------------------
+  int dtype_, esz_, device_, nv_, ne_;
+  std::vector<int> eu_, ev_, phys_, bond_;
+  std::vector<std::vector<Leg>> inc_;
+  std::vector<int> seq_;  // default BP edge sequence (src,dst pairs)
+  bool is_tree_ = false;
+
+  // ---- device-resident state ----------------------------------------------------------------
+  std::vector<void*> site_;     // [nv]  T_v[s, l_0 …] row-major
+  std::vector<void*> msg_;      // [2*ne] directed edge 2e (eu→ev), 2e+1 (ev→eu): χ×χ [ket][bra]
+  std::vector<void*> msg_next_; // staging for a BP level
+  std::vector<int> msg_dim_;    // χ the buffer currently holds (0: not materialised)
+  std::vector<int> msg_next_dim_;
+  std::vector<std::vector<int>> sshape_;  // bond-leg dims each site buffer was written with
+  std::vector<char> msg_set_;   // 0: identity default (messages(bpc) is empty for it)
+  cudaStream_t stream_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+  std::vector<void*> temps_;    // stream-ordered temporaries freed by free_temps()
+  tnqs_stats stats_{};
+  bool profiling_ = false;
+
+  // ---- helpers -------------------------------------------------------------------------------
+  void* dalloc(size_t bytes);
+  void* talloc(size_t bytes);  // temporary, freed by free_temps()
+  void dfree(void* p);
+  void free_temps();
+  template <class T> T* upload(const std::vector<T>& v);
+  int dedge(int src, int dst) const;
+  int leg_pos(int v, int e) const;
+  long long site_elems(int v) const;
+  void leg_view(int v, int pos, unsigned* outer, int* chi, unsigned* inner) const;
+  void materialize_message(int de);
+  void check_shapes() const;
+  size_t scratch_budget() const;
+  bool c64() const { return dtype_ == TNQS_C64; }
+
+  void launch_mode(std::vector<ModeTask>& tasks);
+  void launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vector<double2*>& outs,
+                   bool transpose);
+  void launch_jacobi(std::vector<JacobiTask>& tasks);
+  void run_chains(std::vector<Chain>& chains);
+  ModeTask mode_task(int v, int pos, const void* in, void* out, const void* mat) const;
+  GramTask gram_task(int v, int pos, int planes, const void* X, const void* Y) const;
+
+  void normalize_sites(const std::vector<int>& vs);
+  void apply_one_site_batch(const std::vector<std::pair<int, std::vector<std::complex<double>>>>& g,
+                            bool normalize);
+  void apply_two_site_batch(const std::vector<int>& gate_ids, const int32_t* verts,
+                            const double* mats, const std::vector<size_t>& mat_off,
+                            const tnqs_apply_opts& ao, double* errs);
+  std::vector<std::vector<int>> bp_levels(const std::vector<int>& seq) const;
+  void bp_level(const std::vector<int>& seq, const std::vector<int>& items, double* d_diff);
+  void count_launch(int n = 1) { stats_.kernel_launches += n; }
+  friend struct ProfScope;
+};
+
+}  // namespace tnqs

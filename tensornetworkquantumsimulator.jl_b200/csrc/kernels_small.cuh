@@ -1,0 +1,489 @@
+// kernels_small.cuh — the O(χ³) dense algebra of the path, batched one CTA per matrix, all in
+// fp64 regardless of the state's scalar type (the reference itself promotes the message
+// eigendecomposition to Float64: src/utils.jl:94-108).
+//
+//   jacobi_kernel        one-sided (Hestenes) Jacobi with round-robin pair ordering: complex SVD of
+//                        θ (simple_update.jl:53-59), Hermitian eigendecomposition of BP messages
+//                        (utils.jl:18-35) and of the reduced-factor Gram matrix (replaces the QR at
+//                        simple_update.jl:47-48)
+//   msg_* / su_* / bp_*  glue between the tensor-streaming kernels and the factorizations
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kernels_tensor.cuh"
+
+namespace tnqs {
+
+__device__ __forceinline__ double2 z_mul(const double2 a, const double2 b) {
+  double2 r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// block-wide sum of one double; every thread gets the result.  `red` needs ≥ 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    double s = lane < nw ? red[lane] : 0.0;
+    s = warp_sum(s);
+    if (lane == 0) red[32] = s;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-sided Jacobi
+// ------------------------------------------------------------------------------------------------
+struct JacobiTask {
+  double2* A;    // m×n column-major, overwritten by A·V (columns = σ_j u_j)
+  double2* V;    // n×n column-major accumulated right rotations, or nullptr
+  int m, n;
+  double* sval;  // [n] column norms of the result
+  int* perm;     // [n] column indices by descending sval
+};
+
+__global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restrict__ tasks,
+                                                      int max_sweeps, double tol) {
+  const JacobiTask t = tasks[blockIdx.x];
+  const int n = t.n, m = t.m;
+  const int ne = n + (n & 1);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double2* __restrict__ A = t.A;
+  double2* __restrict__ V = t.V;
+  __shared__ int s_rot;
+  const double tol2 = tol * tol;
+  if (n >= 2) {
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+      if (threadIdx.x == 0) s_rot = 0;
+      __syncthreads();
+      for (int step = 0; step < ne - 1; ++step) {
+        for (int pair = warp; pair < ne / 2; pair += nwarps) {
+          int p, q;
+          if (pair == 0) { p = step; q = ne - 1; }
+          else { p = (step + pair) % (ne - 1); q = (step - pair + (ne - 1)) % (ne - 1); }
+          if (p >= n || q >= n) continue;
+          if (p > q) { const int tmp = p; p = q; q = tmp; }
+          double2* __restrict__ ap = A + (long long)p * m;
+          double2* __restrict__ aq = A + (long long)q * m;
+          double a = 0, b = 0, gx = 0, gy = 0;
+          for (int i = lane; i < m; i += 32) {
+            const double2 x = ap[i], y = aq[i];
+            a += x.x * x.x + x.y * x.y;
+            b += y.x * y.x + y.y * y.y;
+            gx += x.x * y.x + x.y * y.y;   // conj(x)*y
+            gy += x.x * y.y - x.y * y.x;
+          }
+          a = warp_sum(a); b = warp_sum(b); gx = warp_sum(gx); gy = warp_sum(gy);
+          const double g2 = gx * gx + gy * gy;
+          if (g2 > tol2 * a * b && g2 > 0.0) {
+            if (lane == 0) s_rot = 1;
+            const double g = sqrt(g2);
+            const double zeta = (b - a) / (2.0 * g);
+            const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+            double2 ph; ph.x = gx / g; ph.y = -gy / g;  // e^{-iφ}
+            for (int i = lane; i < m; i += 32) {
+              const double2 x = ap[i];
+              const double2 y = z_mul(aq[i], ph);
+              double2 xn, yn;
+              xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+              yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+              ap[i] = xn; aq[i] = yn;
+            }
+            if (V) {
+              double2* __restrict__ vp = V + (long long)p * n;
+              double2* __restrict__ vq = V + (long long)q * n;
+              for (int i = lane; i < n; i += 32) {
+                const double2 x = vp[i];
+                const double2 y = z_mul(vq[i], ph);
+                double2 xn, yn;
+                xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+                yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+                vp[i] = xn; vq[i] = yn;
+              }
+            }
+          }
+        }
+        __syncthreads();
+      }
+      const int rot = s_rot;
+      __syncthreads();
+      if (!rot) break;
+    }
+  }
+  // column norms, then rank sort (descending, ties by index)
+  for (int j = warp; j < n; j += nwarps) {
+    double a = 0;
+    const double2* aj = A + (long long)j * m;
+    for (int i = lane; i < m; i += 32) { const double2 x = aj[i]; a += x.x * x.x + x.y * x.y; }
+    a = warp_sum(a);
+    if (lane == 0) t.sval[j] = sqrt(a);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double sj = t.sval[j];
+    int rank = 0;
+    for (int i = 0; i < n; ++i) {
+      const double si = t.sval[i];
+      rank += (si > sj) || (si == sj && i < j);
+    }
+    t.perm[rank] = j;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BP message → (√M, projector) for the simple-update gauge (simple_update.jl:38-41, utils.jl:18-26)
+// ------------------------------------------------------------------------------------------------
+struct MsgEigTask {
+  const void* M;   // χ×χ row-major message, tensor scalar type
+  double2* A;      // χ×χ column-major work (Hermitian part of M, then M·V)
+  double2* V;      // χ×χ column-major
+  void* sqrtM;     // out: Q √D Q†, row-major, tensor scalar type
+  void* proj;      // out: Q 1[kept] Q†, row-major, tensor scalar type
+  int chi;
+  int* flags;      // out: [0] = projector is the identity, [1] = DomainError (negative eigenvalue ≥ cutoff)
+  double* lam;     // work [χ]
+};
+
+template <typename R>
+__global__ void msg_prepare_kernel(const MsgEigTask* __restrict__ tasks) {
+  using C = typename Cx<R>::type;
+  const MsgEigTask t = tasks[blockIdx.x];
+  const C* __restrict__ M = (const C*)t.M;
+  const int n = t.chi;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx % n, j = idx / n;  // column-major target
+    const C a = M[i * n + j], b = M[j * n + i];
+    double2 h; h.x = 0.5 * ((double)a.x + (double)b.x); h.y = 0.5 * ((double)a.y - (double)b.y);
+    t.A[idx] = h;
+    double2 v; v.x = (i == j) ? 1.0 : 0.0; v.y = 0.0;
+    t.V[idx] = v;
+  }
+}
+
+template <typename R>
+__global__ void msg_finish_kernel(const MsgEigTask* __restrict__ tasks, double cutoff) {
+  using C = typename Cx<R>::type;
+  const MsgEigTask t = tasks[blockIdx.x];
+  const int n = t.chi;
+  __shared__ int s_allkept, s_domain;
+  if (threadIdx.x == 0) { s_allkept = 1; s_domain = 0; }
+  __syncthreads();
+  // λ_j = Re(v_j† (H v_j))
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    double l = 0;
+    for (int i = 0; i < n; ++i) {
+      const double2 v = t.V[i + (long long)j * n], a = t.A[i + (long long)j * n];
+      l += v.x * a.x + v.y * a.y;
+    }
+    const bool kept = !(l == 0.0 || fabs(l) < cutoff);
+    if (!kept) s_allkept = 0;
+    if (kept && l < 0) { s_domain = 1; l = 0; }
+    t.lam[j] = kept ? l : 0.0;
+  }
+  __syncthreads();
+  C* __restrict__ S = (C*)t.sqrtM;
+  C* __restrict__ P = (C*)t.proj;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int a = idx / n, b = idx - a * n;  // row-major [a][b]
+    double sx = 0, sy = 0, px = 0, py = 0;
+    for (int j = 0; j < n; ++j) {
+      const double l = t.lam[j];
+      if (l <= 0) continue;
+      const double2 va = t.V[a + (long long)j * n], vb = t.V[b + (long long)j * n];
+      const double rx = va.x * vb.x + va.y * vb.y;  // va * conj(vb)
+      const double ry = va.y * vb.x - va.x * vb.y;
+      const double f = sqrt(l);
+      sx += f * rx; sy += f * ry; px += rx; py += ry;
+    }
+    C s; s.x = (R)sx; s.y = (R)sy;
+    C p; p.x = (R)px; p.y = (R)py;
+    S[idx] = s; P[idx] = p;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { t.flags[0] = s_allkept; t.flags[1] = s_domain; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// simple-update reduced factors
+// ------------------------------------------------------------------------------------------------
+struct HermTask {
+  const double2* G;  // n×n row-major
+  double2* A;        // n×n column-major Hermitian part
+  double2* V;        // identity
+  int n;
+};
+__global__ void herm_prepare_kernel(const HermTask* __restrict__ tasks) {
+  const HermTask t = tasks[blockIdx.x];
+  const int n = t.n;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int i = idx % n, j = idx / n;
+    const double2 a = t.G[(long long)i * n + j], b = t.G[(long long)j * n + i];
+    double2 h; h.x = 0.5 * (a.x + b.x); h.y = 0.5 * (a.y - b.y);
+    t.A[idx] = h;
+    double2 v; v.x = (i == j) ? 1.0 : 0.0; v.y = 0.0;
+    t.V[idx] = v;
+  }
+}
+
+struct SuGateTask {
+  // per site: eigen-decomposition of the Gram matrix of the gauged tensor (n = d·χ_b)
+  const double2* GA[2];  // G·V (column-major) after Jacobi
+  const double2* GV[2];  // V
+  double* sq[2];         // out [n]: √λ_r (0 for dropped directions)
+  double* isq[2];        // out [n]: 1/√λ_r (0 for dropped)
+  int d[2];
+  int chi_b;
+  int full;              // number of singular values the reference's thin QR leaves: min_s(r_s·d_s)
+  double2 gate[256];     // (d0·d1)² row-major [(s0',s1')][(s0,s1)]
+  double2* theta;        // (n0·d0)×(n1·d1) column-major, Jacobi work
+  double2* theta0;       // copy kept for the right factor
+  // after the θ Jacobi
+  const double* sval;    // [n1·d1]
+  const int* perm;
+  double* sigma;         // out [n1·d1] singular values, descending
+  int* keep;             // out
+  double* err;           // out
+  double* sumsq_kept;    // out Σ kept σ²
+  double2* Rp;           // work (n1·d1) × keep_max
+  void* X[2];            // out: [(s,b)][(s',c)] row-major, tensor scalar type
+};
+
+// λ, R = Λ^{1/2}V† and θ = gate·(R_0 ⊗_b R_1)   (simple_update.jl:47-51 with R†R = Gram)
+__global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tolG) {
+  const SuGateTask& t = tasks[blockIdx.x];
+  __shared__ double red[34];
+  const int chi = t.chi_b;
+  for (int site = 0; site < 2; ++site) {
+    const int n = t.d[site] * chi;
+    const double2* __restrict__ GA = t.GA[site];
+    const double2* __restrict__ GV = t.GV[site];
+    double lmax = 0;
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+      double l = 0;
+      for (int i = 0; i < n; ++i) {
+        const double2 v = GV[i + (long long)r * n], a = GA[i + (long long)r * n];
+        l += v.x * a.x + v.y * a.y;
+      }
+      t.sq[site][r] = l;  // stash λ
+      lmax = fmax(lmax, l);
+    }
+    __syncthreads();  // block-wide max of λ
+    double mx = lmax;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double m2 = 0;
+      for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) m2 = fmax(m2, red[w]);
+      red[33] = m2;
+    }
+    __syncthreads();
+    const double thr = tolG * red[33];
+    for (int r = threadIdx.x; r < n; r += blockDim.x) {
+      const double l = t.sq[site][r];
+      const bool kept = l > thr && l > 0;
+      t.sq[site][r] = kept ? sqrt(l) : 0.0;
+      t.isq[site][r] = kept ? 1.0 / sqrt(l) : 0.0;
+    }
+    __syncthreads();
+  }
+  const int d0 = t.d[0], d1 = t.d[1];
+  const int n0 = d0 * chi, n1 = d1 * chi;
+  const int rows = n0 * d0, cols = n1 * d1;
+  const double2* __restrict__ V0 = t.GV[0];
+  const double2* __restrict__ V1 = t.GV[1];
+  for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+    const int rho = idx % rows, kap = idx / rows;
+    const int r0 = rho / d0, s0p = rho - r0 * d0;
+    const int r1 = kap / d1, s1p = kap - r1 * d1;
+    const double w = t.sq[0][r0] * t.sq[1][r1];
+    double2 acc; acc.x = 0; acc.y = 0;
+    if (w != 0.0) {
+      for (int s0 = 0; s0 < d0; ++s0)
+        for (int s1 = 0; s1 < d1; ++s1) {
+          const double2 g = t.gate[(s0p * d1 + s1p) * (d0 * d1) + (s0 * d1 + s1)];
+          if (g.x == 0.0 && g.y == 0.0) continue;
+          // Σ_b conj(V0[(s0,b), r0]) conj(V1[(s1,b), r1])
+          double wx = 0, wy = 0;
+          const double2* v0 = V0 + (long long)r0 * n0 + s0 * chi;
+          const double2* v1 = V1 + (long long)r1 * n1 + s1 * chi;
+          for (int b = 0; b < chi; ++b) {
+            const double2 x = v0[b], y = v1[b];
+            wx += x.x * y.x - x.y * y.y;
+            wy -= x.x * y.y + x.y * y.x;
+          }
+          acc.x += g.x * wx - g.y * wy;
+          acc.y += g.x * wy + g.y * wx;
+        }
+      acc.x *= w; acc.y *= w;
+    }
+    t.theta[idx] = acc;
+    t.theta0[idx] = acc;
+  }
+}
+
+// NDTensors truncate! on P = σ² (simple_update.jl:53-59): maxdim first, then the relative cutoff
+__global__ void su_truncate_kernel(const SuGateTask* __restrict__ tasks, int ntasks, int maxdim,
+                                   int mindim, double cutoff) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= ntasks) return;
+  const SuGateTask& t = tasks[g];
+  const int n = t.d[1] * t.chi_b * t.d[1];
+  const int full = t.full;  // ≤ min(rows, cols); the columns beyond are structurally zero
+  double total = 0;
+  for (int k = 0; k < n; ++k) {
+    const double s = t.sval[t.perm[k]];
+    t.sigma[k] = s;
+    if (k < full) total += s * s;
+  }
+  const double scale = total > 0 ? total : 1.0;
+  int keep = full;
+  double disc = 0;
+  if (mindim < 1) mindim = 1;
+  if (maxdim > 0) {
+    const int lim = maxdim > mindim ? maxdim : mindim;
+    while (keep > lim && keep > 0) { const double s = t.sigma[keep - 1]; disc += s * s; --keep; }
+  }
+  if (cutoff >= 0) {
+    while (keep > mindim) {
+      const double s = t.sigma[keep - 1];
+      if (disc + s * s <= cutoff * scale) { disc += s * s; --keep; } else break;
+    }
+  }
+  double kept = 0;
+  for (int k = 0; k < keep; ++k) kept += t.sigma[k] * t.sigma[k];
+  *t.keep = keep;
+  *t.err = disc / scale;
+  *t.sumsq_kept = kept;
+}
+
+// X_0 = V_0 Λ_0^{-1/2} · U√σ,  X_1 = V_1 Λ_1^{-1/2} · conj(V_θ)√σ  (simple_update.jl:53-64 folded:
+// T' = (T ×_ext P) · R⁺ · new factor)
+template <typename R>
+__global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
+  using C = typename Cx<R>::type;
+  const SuGateTask& t = tasks[blockIdx.x];
+  const int chi = t.chi_b, d0 = t.d[0], d1 = t.d[1];
+  const int n0 = d0 * chi, n1 = d1 * chi;
+  const int rows = n0 * d0, cols = n1 * d1;
+  const int keep = *t.keep;
+  // right factor: Rp[κ, c] = Σ_ρ θ0[ρ,κ] conj(Uσ[ρ, perm c]) / σ_c^{3/2}
+  for (int idx = threadIdx.x; idx < cols * keep; idx += blockDim.x) {
+    const int kap = idx % cols, c = idx / cols;
+    const double sg = t.sigma[c];
+    double2 acc; acc.x = 0; acc.y = 0;
+    if (sg > 0) {
+      const double2* th = t.theta0 + (long long)kap * rows;
+      const double2* u = t.theta + (long long)t.perm[c] * rows;
+      for (int rho = 0; rho < rows; ++rho) {
+        const double2 a = th[rho], b = u[rho];
+        acc.x += a.x * b.x + a.y * b.y;
+        acc.y += a.y * b.x - a.x * b.y;
+      }
+      const double f = 1.0 / (sg * sqrt(sg));
+      acc.x *= f; acc.y *= f;
+    }
+    t.Rp[idx] = acc;
+  }
+  __syncthreads();
+  // X_0[(s,b),(s0',c)] = Σ_r V0[(s,b),r] isq0[r] · Uσ[(r,s0'), perm c]/√σ_c
+  {
+    C* __restrict__ X = (C*)t.X[0];
+    const int mm = d0 * keep;
+    for (int idx = threadIdx.x; idx < n0 * mm; idx += blockDim.x) {
+      const int row = idx / mm, col = idx - row * mm;
+      const int sp = col / keep, c = col - sp * keep;
+      const double sg = t.sigma[c];
+      double2 acc; acc.x = 0; acc.y = 0;
+      if (sg > 0) {
+        const double2* u = t.theta + (long long)t.perm[c] * rows;
+        for (int r = 0; r < n0; ++r) {
+          const double w = t.isq[0][r];
+          if (w == 0.0) continue;
+          const double2 v = t.GV[0][row + (long long)r * n0];
+          const double2 l = u[r * d0 + sp];
+          acc.x += w * (v.x * l.x - v.y * l.y);
+          acc.y += w * (v.x * l.y + v.y * l.x);
+        }
+        const double f = 1.0 / sqrt(sg);
+        acc.x *= f; acc.y *= f;
+      }
+      C o; o.x = (R)acc.x; o.y = (R)acc.y;
+      X[idx] = o;
+    }
+  }
+  {
+    C* __restrict__ X = (C*)t.X[1];
+    const int mm = d1 * keep;
+    for (int idx = threadIdx.x; idx < n1 * mm; idx += blockDim.x) {
+      const int row = idx / mm, col = idx - row * mm;
+      const int sp = col / keep, c = col - sp * keep;
+      double2 acc; acc.x = 0; acc.y = 0;
+      for (int r = 0; r < n1; ++r) {
+        const double w = t.isq[1][r];
+        if (w == 0.0) continue;
+        const double2 v = t.GV[1][row + (long long)r * n1];
+        const double2 l = t.Rp[(r * d1 + sp) + (long long)c * cols];
+        acc.x += w * (v.x * l.x - v.y * l.y);
+        acc.y += w * (v.x * l.y + v.y * l.x);
+      }
+      C o; o.x = (R)acc.x; o.y = (R)acc.y;
+      X[idx] = o;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BP message finalisation: sum-normalise, convergence measure, write
+// (abstractbeliefpropagationcache.jl:182-187, beliefpropagationcache.jl:17-21)
+// ------------------------------------------------------------------------------------------------
+struct BpFinTask {
+  const double2* g;  // χ×χ row-major un-normalised new message m[l][l']
+  const void* old_msg;
+  void* new_msg;
+  double* diff;      // out: 1 − |⟨new,old⟩|²/(‖new‖²‖old‖²)
+  int chi;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(256) bp_finalize_kernel(const BpFinTask* __restrict__ tasks) {
+  using C = typename Cx<R>::type;
+  const BpFinTask t = tasks[blockIdx.x];
+  __shared__ double red[34];
+  const int n2 = t.chi * t.chi;
+  double sx = 0, sy = 0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) { sx += t.g[i].x; sy += t.g[i].y; }
+  sx = block_sum(sx, red);
+  sy = block_sum(sy, red);
+  // m / Σm unless the sum is exactly zero
+  double ix = 1.0, iy = 0.0;
+  if (sx != 0.0 || sy != 0.0) { const double nn = sx * sx + sy * sy; ix = sx / nn; iy = -sy / nn; }
+  const C* __restrict__ old = (const C*)t.old_msg;
+  C* __restrict__ nw = (C*)t.new_msg;
+  double dx = 0, dy = 0, na = 0, nb = 0;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const double2 g = t.g[i];
+    C v; v.x = (R)(g.x * ix - g.y * iy); v.y = (R)(g.x * iy + g.y * ix);
+    nw[i] = v;
+    const C o = old[i];
+    const double ax = v.x, ay = v.y, bx = o.x, by = o.y;
+    dx += ax * bx + ay * by;  // conj(a)*b
+    dy += ax * by - ay * bx;
+    na += ax * ax + ay * ay;
+    nb += bx * bx + by * by;
+  }
+  dx = block_sum(dx, red); dy = block_sum(dy, red);
+  na = block_sum(na, red); nb = block_sum(nb, red);
+  if (threadIdx.x == 0) *t.diff = 1.0 - (dx * dx + dy * dy) / (na * nb);
+}
+
+}  // namespace tnqs

@@ -1,0 +1,231 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on the same inputs.
+
+Tolerances (stated per north_star): ComplexF64 states must agree with the complex128 oracle to
+1e-9 relative or better; ComplexF32 states are compared with the complex128 oracle at 2e-4 on
+short circuits (fp32 round-off of a different but equivalent operation order; the oracle run in
+complex64 differs from its own complex128 run by the same order) and at 1e-5 on single kernels."""
+import numpy as np
+import pytest
+
+import tnqs_b200 as tq
+from oracle import tnqs_oracle as orc
+from helpers import (X, Y, Z, circuit_for_oracle, oracle_from_bpc, oracle_from_tns, ragged_state,
+                     random_psd_messages, rel, seq_idx, state_overlap, tfim_layer)
+
+pytestmark = pytest.mark.gpu
+
+DT = [(np.complex128, 1e-10), (np.complex64, 2e-5)]
+
+
+def small_graphs():
+    return [tq.named_grid((3, 3)), tq.named_comb_tree((3, 2)), tq.named_path_graph(2), tq.named_grid((2, 2, 2))]
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_site_and_message_roundtrip(dtype, tol):
+    g = tq.named_grid((3, 2))
+    dims = [2, 3, 4, 5, 2, 3, 4][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=3)
+    bpc = tq.BeliefPropagationCache(psi)
+    assert not bpc.messages()  # empty right after construction (test_beliefpropagation.jl:18)
+    for v in g.vertices():
+        assert np.array_equal(bpc.site(v), psi[v])
+    assert list(bpc.bond_dims()) == dims
+    ms = random_psd_messages(g, dims, dtype)
+    bpc.setmessages(list(ms), list(ms.values()))  # test_beliefpropagation.jl:72-82
+    got = bpc.messages()
+    assert set(got) == set(ms)
+    for e in ms:
+        assert np.array_equal(got[e], ms[e])
+    e0 = g.edges[0]
+    assert np.array_equal(tq.BeliefPropagationCache(psi).message(e0), np.eye(dims[0], dtype=dtype))
+    c2 = bpc.copy()
+    assert np.array_equal(c2.site(g.vertices()[1]), psi[g.vertices()[1]])
+    assert np.array_equal(c2.message(e0), ms[e0])
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_expect_with_given_messages(dtype, tol):
+    # exercises the mode-product kernel on every leg position and the Gram kernel (ragged dims)
+    for g in small_graphs():
+        dims = [2 + (3 * e) % 4 for e in range(g.ne)]
+        psi = ragged_state(g, dims, dtype, seed=5)
+        bpc = tq.BeliefPropagationCache(psi)
+        ms = random_psd_messages(g, dims, dtype)
+        bpc.setmessages(list(ms), list(ms.values()))
+        c = oracle_from_tns(psi)
+        for (a, b), m in ms.items():
+            c.msg[(g.index[a], g.index[b])] = m
+        obs = [("Z", [v]) for v in g.vertices()] + [("X", [v], 0.5) for v in g.vertices()]
+        got = tq.expect(bpc, obs)
+        want = [orc.expect_local(c, g.index[v], Z) for v in g.vertices()] + \
+               [orc.expect_local(c, g.index[v], X, 0.5) for v in g.vertices()]
+        assert rel(got, want) < 50 * tol
+        a, b = g.edges[0]
+        got2 = tq.expect(bpc, ("XY", [a, b]))
+        want2 = orc.expect_two_site(c, g.index[a], g.index[b], X, Y)
+        assert abs(got2 - want2) < 50 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+@pytest.mark.parametrize("schedule", ["forest", "bipartite"])
+def test_bp_update_matches_oracle(dtype, tol, schedule):
+    for g in small_graphs():
+        dims = [2 + (e % 3) for e in range(g.ne)]
+        psi = ragged_state(g, dims, dtype, seed=7)
+        seq = tq.forest_cover_edge_sequence(g) if schedule == "forest" else tq.bipartite_edge_sequence(g)
+        bpc = tq.BeliefPropagationCache(psi)
+        out = tq.update(bpc, maxiter=3, edge_sequence=seq)
+        assert not bpc.messages()  # input not mutated (abstractbeliefpropagationcache.jl:228)
+        c = oracle_from_tns(psi)
+        c, _ = orc.bp_update(c, seq_idx(g, seq), maxiter=3, tolerance=None)
+        got = out.messages()
+        assert len(got) == 2 * g.ne
+        for (a, b), m in got.items():
+            assert rel(m, c.msg[(g.index[a], g.index[b])]) < 100 * tol, (schedule, a, b)
+        # convergence loop + report
+        out2 = tq.update(bpc, maxiter=200, tolerance=1e-9 if dtype == np.complex64 else 1e-13, edge_sequence=seq)
+        c2, rep = orc.bp_update(oracle_from_tns(psi), seq_idx(g, seq), maxiter=200,
+                                tolerance=1e-9 if dtype == np.complex64 else 1e-13)
+        assert out2.last_bp_report["converged"]
+        assert abs(out2.last_bp_report["niter"] - rep["niter"]) <= (2 if dtype == np.complex64 else 0)
+
+
+@pytest.mark.parametrize("dtype", [np.complex64, np.complex128])
+def test_bp_exact_on_tree(dtype):
+    # /root/reference/test/test_beliefpropagation.jl:31-55
+    g = tq.named_comb_tree((3, 3))
+    psi = tq.random_tensornetworkstate(dtype, g, bond_dimension=2, seed=123)
+    bpc = tq.update(tq.BeliefPropagationCache(psi))
+    assert len(bpc.messages()) == 2 * g.ne
+    assert bpc.last_bp_report["niter"] == 1
+    c = oracle_from_tns(psi)
+    full = orc.to_statevector(c)
+    vc = g.center()[0]
+    i = g.index[vc]
+    rho = np.moveaxis(full, i, 0).reshape(2, -1)
+    rho = rho @ rho.conj().T
+    rho /= np.trace(rho)
+    eps = np.finfo(np.float32 if dtype == np.complex64 else np.float64).eps
+    for name, op in (("Z", Z), ("X", X), ("Y", Y)):
+        assert abs(tq.expect(bpc, (name, [vc])) - np.trace(op @ rho)) <= 20 * eps
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_one_site_gates(dtype, tol):
+    g = tq.named_grid((2, 3))
+    dims = [2, 3, 2, 4, 3, 2, 3][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=9)
+    circ = [("Rx", [v], 0.3 + 0.1 * i) for i, v in enumerate(g.vertices())] + [("H", [g.vertices()[0]]), ("Ry", g.vertices()[1], 0.7)]
+    for norm in (False, True):
+        bpc = tq.BeliefPropagationCache(psi)
+        out, errs = tq.apply_gates(circ, bpc, apply_kwargs=dict(normalize_tensors=norm), update_cache=False)
+        assert np.all(errs == 0)
+        c = oracle_from_tns(psi)
+        gm, gv = circuit_for_oracle(g, circ)
+        c, _, _ = orc.apply_gates(c, gm, gv, [], dict(normalize_tensors=norm), update_cache=False)
+        for i, v in enumerate(g.vertices()):
+            assert rel(out.site(v), c.T[i]) < 20 * tol
+        assert np.array_equal(bpc.site(g.vertices()[0]), psi[g.vertices()[0]])  # input untouched
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+@pytest.mark.parametrize("gate", ["Rzz", "CNOT", "Rxxyy", "SWAP"])
+def test_single_two_site_gate(dtype, tol, gate):
+    # one simple update with non-trivial environments; compare gauge-invariant outputs
+    g = tq.named_grid((3, 2))
+    dims = [2, 3, 2, 3, 2, 3, 2][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=11)
+    ms = random_psd_messages(g, dims, dtype, seed=12)
+    for e_id in (0, 3, g.ne - 1):
+        a, b = g.edges[e_id]
+        for (maxdim, cutoff) in ((None, None), (3, 1e-12), (2, None)):
+            bpc = tq.BeliefPropagationCache(psi)
+            bpc.setmessages(list(ms), list(ms.values()))
+            circ = [(gate, [a, b], 0.37)] if gate.startswith("R") else [(gate, [a, b])]
+            kw = dict(normalize_tensors=True)
+            if maxdim:
+                kw["maxdim"] = maxdim
+            if cutoff:
+                kw["cutoff"] = cutoff
+            out, errs = tq.apply_gates(circ, bpc, apply_kwargs=kw, update_cache=False)
+            c = oracle_from_tns(psi)
+            for (x, y), m in ms.items():
+                c.msg[(g.index[x], g.index[y])] = m
+            gm, gv = circuit_for_oracle(g, circ)
+            c, oerrs, _ = orc.apply_gates(c, gm, gv, [], kw, update_cache=False)
+            assert out.bond_dims()[e_id] == c.bond_dims()[e_id]
+            assert abs(errs[0] - oerrs[0]) <= 200 * tol * max(oerrs[0], 1e-3)
+            assert rel(np.diag(out.message((a, b))), np.diag(c.msg[(g.index[a], g.index[b])])) < 100 * tol
+            assert np.array_equal(out.message((a, b)), out.message((b, a)))
+            ov, n1, n2 = state_overlap(oracle_from_bpc(out), c)
+            assert abs(ov - 1) < 100 * tol and abs(n1 / n2 - 1) < 100 * tol
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_tfim_layers_small_grid(dtype, tol):
+    # test_apply.jl:23-53 flavour with truncation: per-gate truncerr, ⟨Z⟩, bond dims, messages
+    g = tq.named_grid((3, 3))
+    layer = tfim_layer(g)
+    seq = tq.bipartite_edge_sequence(g)
+    bptol = 1e-13 if dtype == np.complex128 else 1e-10
+    kw = dict(maxdim=3, cutoff=1e-12, normalize_tensors=True)
+    bp = dict(maxiter=300, tolerance=bptol, edge_sequence=seq)
+    psi = tq.BeliefPropagationCache(tq.zerostate(dtype, g))
+    c = orc.product_state(g.nv, g.edge_uv(), [(1.0, 0.0)] * g.nv, np.complex128)
+    gm, gv = circuit_for_oracle(g, layer)
+    ftol = tol if dtype == np.complex128 else 10 * tol
+    for layer_i in range(4):
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)
+        c, oerrs, reps = orc.apply_gates(c, gm, gv, seq_idx(g, seq), kw, dict(maxiter=300, tolerance=1e-13))
+        assert len(psi.last_bp_reports) == len(reps) == 5
+        assert list(psi.bond_dims()) == c.bond_dims()
+        assert np.max(np.abs(errs - oerrs)) <= 100 * ftol * max(np.max(oerrs), 1e-6), layer_i
+        zs = tq.expect(psi, [("Z", [v]) for v in g.vertices()])
+        zo = [orc.expect_local(c, i, Z) for i in range(g.nv)]
+        assert np.max(np.abs(np.array(zs) - np.array(zo))) < 100 * ftol, layer_i
+    assert psi.maxvirtualdim() <= 3
+
+
+def test_example_2d_ising_dynamics_plumbing_config():
+    """BASELINE config 1: examples/2dIsing_dynamics.jl (5×5, dt=.25, hx=1, hz=.8, J=.5) with
+    maxdim=4 / ComplexF64 per BASELINE.json, default BP kwargs, 6 layers, vs the oracle."""
+    g = tq.named_grid((5, 5))
+    layer = tfim_layer(g)
+    kw = dict(maxdim=4, cutoff=1e-10, normalize_tensors=False)
+    psi = tq.BeliefPropagationCache(tq.tensornetworkstate(np.complex128, lambda v: "↑", g, "S=1/2"))
+    c = orc.product_state(g.nv, g.edge_uv(), [(1.0, 0.0)] * g.nv, np.complex128)
+    seq = tq.forest_cover_edge_sequence(g)
+    gm, gv = circuit_for_oracle(g, layer)
+    for l in range(6):
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw)
+        c, oerrs, _ = orc.apply_gates(c, gm, gv, seq_idx(g, seq), kw)
+        sz = tq.expect(psi, ("Z", [(3, 3)]))
+        so = orc.expect_local(c, g.index[(3, 3)], Z)
+        assert psi.maxvirtualdim() == c.maxvirtualdim() <= 4
+        assert abs(sz - so) < 1e-7, (l, sz, so)
+        assert np.max(np.abs(errs - oerrs)) < 1e-7 * max(1.0, np.max(oerrs) / 1e-3), l
+
+
+def test_error_conventions():
+    g = tq.named_grid((2, 2))
+    psi = tq.BeliefPropagationCache(tq.zerostate(np.complex64, g))
+    with pytest.raises(tq.TnqsError) as ei:  # apply_gates.jl:114-120
+        tq.apply_gates([("Rzz", [(1, 1), (2, 2)], 0.1)], psi)
+    assert ei.value.code == 2
+    with pytest.raises(tq.ArgumentError):    # gate_definitions.jl:131-140
+        tq.apply_gates([("Rqq", [(1, 1), (2, 1)], 0.1)], psi)
+    assert tq.expect(psi, ("Z", [(1, 1)], 0.0)) == 0
+    assert abs(tq.expect(psi, ("Z", [(1, 1)])) - 1) < 1e-6
+
+
+def test_two_qubit_circuit_invariants():
+    # /root/reference/test/test_apply.jl:11-20
+    circuit = [("Rx", [(1, 1)], 0.5), ("Rx", [(2, 1)], 0.2), ("CPHASE", [(1, 1), (2, 1)], -0.3)]
+    g = tq.build_graph_from_circuit(circuit)
+    psi0 = tq.tensornetworkstate(np.complex64, lambda v: "↓", g)
+    psi, _ = tq.apply_circuit(circuit, psi0, apply_kwargs=dict(maxdim=2, cutoff=1e-10, normalize_tensors=False))
+    assert isinstance(psi, tq.TensorNetworkState) and psi.scalartype() == np.complex64
+    assert psi.maxvirtualdim() <= 2
+    full = orc.to_statevector(oracle_from_tns(psi))
+    assert abs(np.vdot(full, full) - 1) < 1e-5

@@ -235,7 +235,7 @@ def run_ours(args):
     # every launch group with events on the launching stream; done on one extra, untimed layer)
     psi.set_profiling(True)
     psi.stats(reset=True)
-    psi2, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)
+    psi2, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True)
     sp = psi2.stats()
     psi.set_profiling(False)
     pk = peaks()

@@ -58,7 +58,28 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restri
   double2* __restrict__ A = t.A;
   double2* __restrict__ V = t.V;
   __shared__ int s_rot;
+  __shared__ double s_part[32];
+  __shared__ double s_floor;
   const double tol2 = tol * tol;
+  // Columns whose norm falls below 1e-20·‖A‖_F are numerically null (rank-deficient θ / Gram
+  // matrices): rotating them only chases round-off and never terminates, so they are left alone.
+  {
+    double part = 0;
+    for (long long idx = threadIdx.x; idx < (long long)m * n; idx += blockDim.x) {
+      const double2 x = A[idx];
+      part += x.x * x.x + x.y * x.y;
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_part[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double f = 0;
+      for (int w = 0; w < nwarps; ++w) f += s_part[w];
+      s_floor = 1e-40 * f;
+    }
+    __syncthreads();
+  }
+  const double floor2 = s_floor;
   if (n >= 2) {
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
       if (threadIdx.x == 0) s_rot = 0;
@@ -82,7 +103,7 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restri
           }
           a = warp_sum(a); b = warp_sum(b); gx = warp_sum(gx); gy = warp_sum(gy);
           const double g2 = gx * gx + gy * gy;
-          if (g2 > tol2 * a * b && g2 > 0.0) {
+          if (g2 > tol2 * a * b && a > floor2 && b > floor2) {
             if (lane == 0) s_rot = 1;
             const double g = sqrt(g2);
             const double zeta = (b - a) / (2.0 * g);

@@ -214,6 +214,9 @@ def run_ours(args):
     sampler.start()
     sweeps, e2e_s, dev_ms, zs = 0, 0.0, 0.0, []
     maxerr = 0.0
+    st = {"bp_ms": 0.0, "su_ms": 0.0, "bp_sweeps": 0, "kernel_launches": 0}
+    if args.cuda_profiler:
+        torch.cuda.profiler.start()
     for _ in range(args.steps):
         t0 = time.perf_counter()
         psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)  # public API, host in/out
@@ -222,7 +225,11 @@ def run_ours(args):
         zs.append(float(np.real(z)))
         maxerr = max(maxerr, float(errs.max()))
         sweeps += sum(r["niter"] for r in psi.last_bp_reports)
-    st = psi.stats()
+        s1 = psi.stats()  # the returned cache is a fresh clone: its counters cover exactly this call
+        for k in st:
+            st[k] += s1[k]
+    if args.cuda_profiler:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     dev_ms = st["bp_ms"] + st["su_ms"]  # CUDA events on the engine stream around every apply_gates call
     d2h = int(8 * len(nverts) + 16)
@@ -289,9 +296,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=16)
     ap.add_argument("--chi", type=int, default=32)
-    ap.add_argument("--prep", type=int, default=6, help="untimed layers from the product state before warm-up")
+    ap.add_argument("--prep", type=int, default=15, help="untimed layers from the product state before warm-up")
     ap.add_argument("--schedule", default="bipartite", choices=["bipartite", "forest"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--ref-budget", type=float, default=20.0)
     ap.add_argument("--ref-bp-sweeps", type=float, default=15.0)
     args = ap.parse_args()

@@ -106,6 +106,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : temps_) cudaFreeAsync(p, stream_);
+  for (char* p : arena_) cudaFreeAsync(p, stream_);
   for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
@@ -123,9 +124,24 @@ void* Engine::dalloc(size_t bytes) {
   TNQS_CUDA(cudaMallocAsync(&p, bytes, stream_));
   return p;
 }
+// Temporaries: small ones are bump-allocated from cached 32 MiB chunks (thousands per gate batch —
+// one cudaMallocAsync each would dominate the host time), large ones go to the stream-ordered pool.
 void* Engine::talloc(size_t bytes) {
-  void* p = dalloc(bytes);
-  temps_.push_back(p);
+  constexpr size_t kChunk = 32ull << 20, kSmall = 1ull << 20;
+  if (bytes >= kSmall) {
+    void* p = dalloc(bytes);
+    temps_.push_back(p);
+    return p;
+  }
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  if (arena_cur_ >= arena_.size() || arena_off_ + bytes > kChunk) {
+    if (arena_cur_ < arena_.size() && arena_off_ > 0) ++arena_cur_;
+    if (arena_cur_ >= arena_.size()) arena_.push_back((char*)dalloc(kChunk));
+    arena_off_ = 0;
+  }
+  void* p = arena_[arena_cur_] + arena_off_;
+  arena_off_ += bytes;
   return p;
 }
 void Engine::dfree(void* p) {
@@ -134,6 +150,8 @@ void Engine::dfree(void* p) {
 void Engine::free_temps() {
   for (void* p : temps_) TNQS_CUDA(cudaFreeAsync(p, stream_));
   temps_.clear();
+  arena_cur_ = 0;  // chunks stay cached; reuse is ordered by the single engine stream
+  arena_off_ = 0;
 }
 template <class T> T* Engine::upload(const std::vector<T>& v) {
   T* d = (T*)talloc(v.size() * sizeof(T));
@@ -459,9 +477,18 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks) {
   int maxn = 0;
   for (auto& t : tasks) maxn = std::max(maxn, t.n);
   const int pairs = (maxn + 1) / 2;
-  const int warps = std::max(1, std::min(32, pairs));
+  int maxm = 0;
+  for (auto& t : tasks) maxm = std::max(maxm, std::max(t.m, t.n));
+  const int maxwarps = maxm <= 128 ? 32 : (maxm <= 256 ? 16 : 8);  // register budget per lane grows with m
+  const int warps = std::max(1, std::min(maxwarps, pairs));
   JacobiTask* d = upload(tasks);
-  jacobi_kernel<<<(unsigned)tasks.size(), warps * 32, 0, stream_>>>(d, 60, 1e-15);
+  const unsigned nb = (unsigned)tasks.size();
+  if (maxm <= 32) jacobi_kernel<1><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  else if (maxm <= 64) jacobi_kernel<2><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  else if (maxm <= 128) jacobi_kernel<4><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  else if (maxm <= 256) jacobi_kernel<8><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  else if (maxm <= 512) jacobi_kernel<16><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  else throw Error(TNQS_EINVAL, "matrix too large for the batched Jacobi kernel (max 512 rows)");
   count_launch();
   TNQS_CUDA(cudaGetLastError());
 }

@@ -92,6 +92,8 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   std::vector<void*> temps_;    // stream-ordered temporaries freed by free_temps()
+  std::vector<char*> arena_;    // cached chunks for small temporaries
+  size_t arena_cur_ = 0, arena_off_ = 0;
   tnqs_stats stats_{};
   bool profiling_ = false;
 

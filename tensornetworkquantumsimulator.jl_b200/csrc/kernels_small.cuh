@@ -49,7 +49,10 @@ struct JacobiTask {
   int* perm;     // [n] column indices by descending sval
 };
 
-__global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restrict__ tasks,
+// RPL = rows held per lane: each lane keeps its rows of both columns of a pair in registers, so a
+// pair costs one L2 round trip (all loads issued back to back) instead of one per row chunk.
+template <int RPL>
+__global__ void __launch_bounds__(RPL <= 4 ? 1024 : (RPL == 8 ? 512 : 256)) jacobi_kernel(const JacobiTask* __restrict__ tasks,
                                                       int max_sweeps, double tol) {
   const JacobiTask t = tasks[blockIdx.x];
   const int n = t.n, m = t.m;
@@ -60,7 +63,10 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restri
   __shared__ int s_rot;
   __shared__ double s_part[32];
   __shared__ double s_floor;
-  const double tol2 = tol * tol;
+  __shared__ unsigned char s_dead[512];  // columns already known to be numerically null
+  for (int j = threadIdx.x; j < 512; j += blockDim.x) s_dead[j] = 0;
+  // orthogonality threshold ∝ √m·eps (round-off floor of an m-term dot product, as in LAPACK xGESVJ)
+  const double tol2 = tol * tol * (double)(m > 1 ? m : 1);
   // Columns whose norm falls below 1e-20·‖A‖_F are numerically null (rank-deficient θ / Gram
   // matrices): rotating them only chases round-off and never terminates, so they are left alone.
   {
@@ -90,12 +96,21 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restri
           if (pair == 0) { p = step; q = ne - 1; }
           else { p = (step + pair) % (ne - 1); q = (step - pair + (ne - 1)) % (ne - 1); }
           if (p >= n || q >= n) continue;
+          if (s_dead[p] | s_dead[q]) continue;
           if (p > q) { const int tmp = p; p = q; q = tmp; }
           double2* __restrict__ ap = A + (long long)p * m;
           double2* __restrict__ aq = A + (long long)q * m;
+          double2 xr[RPL], yr[RPL];
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            const int i = lane + 32 * k;
+            if (i < m) { xr[k] = ap[i]; yr[k] = aq[i]; }
+            else { xr[k].x = xr[k].y = 0; yr[k].x = yr[k].y = 0; }
+          }
           double a = 0, b = 0, gx = 0, gy = 0;
-          for (int i = lane; i < m; i += 32) {
-            const double2 x = ap[i], y = aq[i];
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) {
+            const double2 x = xr[k], y = yr[k];
             a += x.x * x.x + x.y * x.y;
             b += y.x * y.x + y.y * y.y;
             gx += x.x * y.x + x.y * y.y;   // conj(x)*y
@@ -103,31 +118,48 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(const JacobiTask* __restri
           }
           a = warp_sum(a); b = warp_sum(b); gx = warp_sum(gx); gy = warp_sum(gy);
           const double g2 = gx * gx + gy * gy;
+          if (lane == 0) {
+            if (!(a > floor2)) s_dead[p] = 1;
+            if (!(b > floor2)) s_dead[q] = 1;
+          }
           if (g2 > tol2 * a * b && a > floor2 && b > floor2) {
             if (lane == 0) s_rot = 1;
-            const double g = sqrt(g2);
-            const double zeta = (b - a) / (2.0 * g);
+            const double ig = rsqrt(g2);
+            const double zeta = 0.5 * (b - a) * ig;
             const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-            const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
-            double2 ph; ph.x = gx / g; ph.y = -gy / g;  // e^{-iφ}
-            for (int i = lane; i < m; i += 32) {
-              const double2 x = ap[i];
-              const double2 y = z_mul(aq[i], ph);
-              double2 xn, yn;
-              xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
-              yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
-              ap[i] = xn; aq[i] = yn;
+            const double c = rsqrt(1.0 + tt * tt), s = c * tt;
+            double2 ph; ph.x = gx * ig; ph.y = -gy * ig;  // e^{-iφ}
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+              const int i = lane + 32 * k;
+              if (i < m) {
+                const double2 x = xr[k];
+                const double2 y = z_mul(yr[k], ph);
+                double2 xn, yn;
+                xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+                yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+                ap[i] = xn; aq[i] = yn;
+              }
             }
             if (V) {
               double2* __restrict__ vp = V + (long long)p * n;
               double2* __restrict__ vq = V + (long long)q * n;
-              for (int i = lane; i < n; i += 32) {
-                const double2 x = vp[i];
-                const double2 y = z_mul(vq[i], ph);
-                double2 xn, yn;
-                xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
-                yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
-                vp[i] = xn; vq[i] = yn;
+#pragma unroll
+              for (int k = 0; k < RPL; ++k) {
+                const int i = lane + 32 * k;
+                if (i < n) { xr[k] = vp[i]; yr[k] = vq[i]; }
+              }
+#pragma unroll
+              for (int k = 0; k < RPL; ++k) {
+                const int i = lane + 32 * k;
+                if (i < n) {
+                  const double2 x = xr[k];
+                  const double2 y = z_mul(yr[k], ph);
+                  double2 xn, yn;
+                  xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+                  yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+                  vp[i] = xn; vq[i] = yn;
+                }
               }
             }
           }

@@ -31,7 +31,7 @@ class Stats(C.Structure):
                 ("bp_messages", C.c_int64), ("two_site_gates", C.c_int64), ("bp_sweeps", C.c_int64),
                 ("mode_ms", C.c_double), ("gram_ms", C.c_double), ("small_ms", C.c_double),
                 ("mode_flops", C.c_double), ("gram_flops", C.c_double),
-                ("mode_launches", C.c_int64), ("gram_launches", C.c_int64)]
+                ("mode_launches", C.c_int64), ("gram_launches", C.c_int64), ("tc_launches", C.c_int64)]
 
 
 class TnqsError(RuntimeError):

@@ -4,6 +4,8 @@
 #include <cstdio>
 #include <numeric>
 #include <set>
+#include <tuple>
+#include <cstdlib>
 
 namespace tnqs {
 
@@ -51,6 +53,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
+  { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
   cudaMemPool_t pool;
   TNQS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thr = UINT64_MAX;
@@ -77,6 +80,8 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
 Engine::Engine(const Engine& o)
     : dtype_(o.dtype_), esz_(o.esz_), device_(o.device_), nv_(o.nv_), ne_(o.ne_), eu_(o.eu_), ev_(o.ev_),
       phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
+  use_tc_ = o.use_tc_;
+  profiling_ = o.profiling_;
   TNQS_CUDA(cudaSetDevice(device_));
   TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   TNQS_CUDA(cudaEventCreate(&ev0_));
@@ -361,9 +366,94 @@ static void launch_mode_variant(const ModeTask* d, int ntasks, int maxtiles, boo
   }
 }
 
-void Engine::launch_mode(std::vector<ModeTask>& tasks) {
-  if (tasks.empty()) return;
+// tcgen05 path for ComplexF32 mode products (kernels_tc.cuh).  Returns the tasks it did not take.
+std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks) {
+  std::vector<ModeTask> rest;
+  if (!c64() || !use_tc_) return tasks;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TNQS_CUDA(cudaFuncSetAttribute(tc::tc_mode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    TNQS_CUDA(cudaFuncSetAttribute(tc::tc_mode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  struct ImgKey { const void* mat; int KK, MM, last; bool operator<(const ImgKey& o) const {
+    return std::tie(mat, KK, MM, last) < std::tie(o.mat, o.KK, o.MM, o.last); } };
+  std::map<ImgKey, float*> images;
+  std::vector<tc::PrepTask> preps;
+  std::vector<tc::TcModeTask> tt[2];
+  std::vector<int> cta_task[2];
+  size_t smem_max[2] = {0, 0};
+  double flops = 0;
+  for (auto& t : tasks) {
+    const bool last = t.inner == 1;
+    const int NNp = (2 * t.MM + 15) / 16 * 16;
+    const int KKf = last ? 2 * t.KK : t.KK;
+    const int nchunk = (KKf + tc::KC - 1) / tc::KC;
+    const size_t b_bytes = (size_t)nchunk * 2 * NNp * tc::KC * 4;
+    bool ok = NNp <= 256 && b_bytes <= 96 * 1024 && (double)t.CC * t.KK >= 8192.0;
+    if (!last) ok = ok && (t.inner % 2 == 0) && (t.ips % 2 == 0) && (t.ops % 2 == 0);
+    ok = ok && ((reinterpret_cast<uintptr_t>(t.in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t.out) & 15) == 0);
+    if (!ok) { rest.push_back(t); continue; }
+    const int P_in = t.KK / t.chi_in, P_out = t.MM / t.chi_out;
+    ImgKey key{t.mat, t.KK, t.MM, last ? 1 : 0};
+    auto it = images.find(key);
+    if (it == images.end()) {
+      float* img = (float*)talloc(b_bytes);
+      tc::PrepTask pt{};
+      pt.mat = (const float2*)t.mat; pt.image = img; pt.KKc = t.KK; pt.MMc = t.MM; pt.NNp = NNp; pt.nchunk = nchunk; pt.last = last ? 1 : 0;
+      preps.push_back(pt);
+      it = images.emplace(key, img).first;
+    }
+    tc::TcModeTask k{};
+    k.in = (const float2*)t.in; k.out = (float2*)t.out; k.image = it->second;
+    k.ips = t.ips; k.ops = t.ops; k.chi_in = t.chi_in; k.chi_out = t.chi_out; k.P_in = P_in; k.P_out = P_out;
+    k.KKc = t.KK; k.MMc = t.MM; k.NNp = NNp; k.nchunk = nchunk; k.outer = t.outer; k.inner = t.inner; k.CC = t.CC;
+    const int cols = last ? 128 : 64;
+    k.ntiles = (int)((t.CC + cols - 1) / cols);
+    const int g = last ? 1 : 0;
+    tt[g].push_back(k);
+    const size_t out_bytes = last ? (size_t)128 * (NNp + 4) * 4 : (size_t)(NNp / 2) * 128 * 4;
+    smem_max[g] = std::max(smem_max[g], ((b_bytes / 4 + 255) & ~size_t(255)) * 4 + 2 * 128 * tc::KC * 4 + out_bytes);
+    flops += 8.0 * t.KK * t.MM * (double)t.CC;
+  }
+  if (tt[0].empty() && tt[1].empty()) return rest;
+  {
+    tc::PrepTask* dp = upload(preps);
+    tc::tc_prep_b_kernel<<<(unsigned)preps.size(), 256, 0, stream_>>>(dp);
+    count_launch();
+  }
+  for (int g = 0; g < 2; ++g) {
+    if (tt[g].empty()) continue;
+    long long total_tiles = 0;
+    for (auto& k : tt[g]) total_tiles += k.ntiles;
+    const int tpc = (int)std::max<long long>(4, std::min<long long>(32, total_tiles / (148 * 8)));
+    int ncta = 0;
+    for (size_t i = 0; i < tt[g].size(); ++i) {
+      auto& k = tt[g][i];
+      k.tiles_per_cta = tpc;
+      k.cta_begin = ncta;
+      const int n = (k.ntiles + tpc - 1) / tpc;
+      for (int c = 0; c < n; ++c) cta_task[g].push_back((int)i);
+      ncta += n;
+    }
+    tc::TcModeTask* dt = upload(tt[g]);
+    int* dc = upload(cta_task[g]);
+    if (g == 0) tc::tc_mode_kernel<false><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+    else tc::tc_mode_kernel<true><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+    count_launch();
+    stats_.mode_launches += 1;
+    stats_.tc_launches += 1;
+  }
+  stats_.mode_flops += flops;
+  TNQS_CUDA(cudaGetLastError());
+  return rest;
+}
+
+void Engine::launch_mode(std::vector<ModeTask>& tasks_in) {
+  if (tasks_in.empty()) return;
   ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.mode_ms);
+  std::vector<ModeTask> tasks = launch_mode_tc(tasks_in);
+  if (tasks.empty()) return;
   for (int pass = 0; pass < 2; ++pass) {
     const bool inner1 = pass == 1;
     std::vector<ModeTask> grp;

@@ -17,6 +17,7 @@
 #include "../../include/tnqs_b200.h"
 #include "kernels_small.cuh"
 #include "kernels_tensor.cuh"
+#include "kernels_tc.cuh"
 
 namespace tnqs {
 
@@ -96,6 +97,7 @@ class Engine {
   size_t arena_cur_ = 0, arena_off_ = 0;
   tnqs_stats stats_{};
   bool profiling_ = false;
+  bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
 
   // ---- helpers -------------------------------------------------------------------------------
   void* dalloc(size_t bytes);
@@ -113,6 +115,7 @@ class Engine {
   bool c64() const { return dtype_ == TNQS_C64; }
 
   void launch_mode(std::vector<ModeTask>& tasks);
+  std::vector<ModeTask> launch_mode_tc(std::vector<ModeTask>& tasks);
   void launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vector<double2*>& outs,
                    bool transpose);
   void launch_jacobi(std::vector<JacobiTask>& tasks);

@@ -229,3 +229,43 @@ def test_two_qubit_circuit_invariants():
     assert psi.maxvirtualdim() <= 2
     full = orc.to_statevector(oracle_from_tns(psi))
     assert abs(np.vdot(full, full) - 1) < 1e-5
+
+
+@pytest.mark.parametrize("chi", [8, 12, 6, 16])
+def test_tensor_core_mode_products(chi):
+    """ComplexF32 mode products on the tcgen05 path (3×TF32): every leg position (MN-major and
+    K-major operand variants), padded shapes (χ not a multiple of 8), against the complex128 oracle.
+    Tolerance 2e-5 relative: 3×TF32 carries ~2^-21 per product, fp32 accumulation in TMEM."""
+    g = tq.named_grid((3, 3))
+    dims = [chi] * g.ne
+    psi = ragged_state(g, dims, np.complex64, seed=21)
+    bpc = tq.BeliefPropagationCache(psi)
+    ms = random_psd_messages(g, dims, np.complex64, seed=22)
+    bpc.setmessages(list(ms), list(ms.values()))
+    c = oracle_from_tns(psi)
+    c.dtype = np.dtype(np.complex128)
+    c.T = [t.astype(np.complex128) for t in c.T]
+    for (a, b), m in ms.items():
+        c.msg[(g.index[a], g.index[b])] = m.astype(np.complex128)
+    bpc.stats(reset=True)
+    got = tq.expect(bpc, [("Z", [v]) for v in g.vertices()] + [("X", [v]) for v in g.vertices()])
+    want = [orc.expect_local(c, i, Z) for i in range(g.nv)] + [orc.expect_local(c, i, X) for i in range(g.nv)]
+    assert np.max(np.abs(np.array(got) - np.array(want))) < 2e-5
+    if chi >= 8:
+        assert bpc.stats()["tc_launches"] > 0  # the tensor-core kernels really ran (tiny shapes stay on SIMT)
+    seq = tq.bipartite_edge_sequence(g)
+    out = tq.update(bpc, maxiter=2, edge_sequence=seq)
+    c2, _ = orc.bp_update(c, seq_idx(g, seq), maxiter=2, tolerance=None)
+    for (a, b), m in out.messages().items():
+        assert rel(m, c2.msg[(g.index[a], g.index[b])]) < 5e-5, (a, b)
+    # one two-site gate (final plane-mixing product on the tensor cores as well)
+    a, b = (2, 2), (2, 3)
+    kw = dict(maxdim=chi, cutoff=1e-12, normalize_tensors=True)
+    out2, errs = tq.apply_gates([("Rzz", [a, b], 0.4)], bpc, apply_kwargs=kw, update_cache=False)
+    gm, gv = circuit_for_oracle(g, [("Rzz", [a, b], 0.4)])
+    c3, oerrs, _ = orc.apply_gates(c, gm, gv, [], kw, update_cache=False)
+    assert abs(errs[0] - oerrs[0]) < 2e-4 * max(oerrs[0], 1e-3)
+    assert rel(np.diag(out2.message((a, b))), np.diag(c3.msg[(g.index[a], g.index[b])])) < 2e-4
+    zs = tq.expect(out2, [("Z", [a]), ("Z", [b])])
+    zo = [orc.expect_local(c3, g.index[a], Z), orc.expect_local(c3, g.index[b], Z)]
+    assert np.max(np.abs(np.array(zs) - np.array(zo))) < 1e-4

@@ -500,13 +500,79 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   if (tasks.empty()) return;
   ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.gram_ms);
   std::vector<ReduceTask> red(tasks.size());
+  std::vector<char> done(tasks.size(), 0);
+  // ---- tcgen05 path: ComplexF32, fp32 accumulation (BP messages), one plane, χ ≤ 64 ------------------
+  if (c64() && use_tc_ && !acc_double) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    std::vector<tc::TcGramTask> tt[2];
+    std::vector<int> ids[2];
+    size_t smem_max[2] = {0, 0};
+    long long work[2] = {0, 0};
+    for (size_t i = 0; i < tasks.size(); ++i) {
+      const GramTask& t = tasks[i];
+      const bool last = t.inner == 1;
+      bool ok = t.MM == t.chi && t.chi <= 64 && t.chi % 2 == 0 && (double)t.CC * t.chi >= 4096.0;
+      if (!last) ok = ok && t.inner % 16 == 0;
+      ok = ok && ((reinterpret_cast<uintptr_t>(t.X) & 15) == 0) && ((reinterpret_cast<uintptr_t>(t.Y) & 15) == 0);
+      if (!ok) continue;
+      tc::TcGramTask k{};
+      k.X = (const float2*)t.X; k.Y = (const float2*)t.Y; k.chi = t.chi;
+      k.MMp = 2 * t.chi <= 64 ? 64 : 128;
+      k.NNp = last ? (2 * t.chi + 31) / 32 * 32 : (t.chi + 15) / 16 * 16;
+      k.outer = t.outer; k.inner = t.inner; k.CC = t.CC;
+      const int g = last ? 1 : 0;
+      tt[g].push_back(k);
+      ids[g].push_back((int)i);
+      smem_max[g] = std::max(smem_max[g], (size_t)2 * (2 * k.MMp + 2 * k.NNp) * tc::KC * 4);
+      work[g] += t.CC;
+      done[i] = 1;
+    }
+    for (int g = 0; g < 2; ++g) {
+      if (tt[g].empty()) continue;
+      const unsigned scols = g ? 32 : 16;
+      // aim at ~8 CTAs per SM overall, at least 512 columns per split
+      const long long target_cols = std::max<long long>(512, work[g] / (148 * 8));
+      std::vector<int> cta_task;
+      int ncta = 0;
+      for (size_t k = 0; k < tt[g].size(); ++k) {
+        tc::TcGramTask& t = tt[g][k];
+        long long ns = std::max<long long>(1, (t.CC + target_cols - 1) / target_cols);
+        ns = std::min<long long>(ns, 4096);
+        unsigned cps = (unsigned)((t.CC + ns - 1) / ns);
+        cps = (cps + scols - 1) / scols * scols;
+        t.cols_per_split = cps;
+        t.nsplit = (int)((t.CC + cps - 1) / cps);
+        t.partial = (double2*)talloc((size_t)t.nsplit * t.chi * t.chi * sizeof(double2));
+        t.cta_begin = ncta;
+        for (int c = 0; c < t.nsplit; ++c) cta_task.push_back((int)k);
+        ncta += t.nsplit;
+        const int i = ids[g][k];
+        ReduceTask& r = red[i];
+        r.partial = t.partial; r.out = outs[i]; r.nsplit = t.nsplit; r.MM = t.chi; r.transpose = transpose ? 1 : 0;
+        stats_.gram_flops += 8.0 * t.chi * t.chi * (double)t.CC;
+      }
+      tc::TcGramTask* dt = upload(tt[g]);
+      int* dc = upload(cta_task);
+      if (g == 0) tc::tc_gram_kernel<false><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+      else tc::tc_gram_kernel<true><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+      count_launch();
+      stats_.gram_launches += 1;
+      stats_.tc_launches += 1;
+      TNQS_CUDA(cudaGetLastError());
+    }
+  }
   for (int pass = 0; pass < 2; ++pass) {
     const bool inner1 = pass == 1;
     std::vector<GramTask> grp;
     std::vector<int> ids;
     int maxMM = 0;
     for (size_t i = 0; i < tasks.size(); ++i)
-      if ((tasks[i].inner == 1) == inner1) { grp.push_back(tasks[i]); ids.push_back((int)i); maxMM = std::max(maxMM, tasks[i].MM); }
+      if (!done[i] && (tasks[i].inner == 1) == inner1) { grp.push_back(tasks[i]); ids.push_back((int)i); maxMM = std::max(maxMM, tasks[i].MM); }
     if (grp.empty()) continue;
     const bool small = maxMM <= 32;
     const int ti = small ? 32 : 64;

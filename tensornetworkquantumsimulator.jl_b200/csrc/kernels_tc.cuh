@@ -385,5 +385,208 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gram:  partial[split][i][j] = Σ_{col ∈ split} conj(X[i][col]) · Y[j][col]      (one plane, i,j < χ ≤ 64)
+// ------------------------------------------------------------------------------------------------
+//   MID  (inner ≥ 16): per outer slice the rows X[i,:], Y[j,:] are K-contiguous real vectors of
+//        (n,ri) floats.  D[(j,part), i] = Σ_k Ycat[(j,part),k] · X[i,k] with Ycat[(j,0)] = Y[j],
+//        Ycat[(j,1)] = (Yi, −Yr) rotated copy built in registers; re = part 0, im = part 1.
+//        Both operands K-major / no swizzle.
+//   LAST (inner == 1): each column is a contiguous row of (i,ri) floats → both operands MN-major
+//        (SWIZZLE_128B_BASE32B).  D[(i,ri),(j,rj)]: re = D[(i,0),(j,0)] + D[(i,1),(j,1)],
+//        im = D[(i,0),(j,1)] − D[(i,1),(j,0)].
+// K is streamed through two shared-memory stages; the accumulator stays in TMEM for the whole split
+// and is drained once.  M is 64 (χ ≤ 32) or 128.
+struct TcGramTask {
+  const float2* X;
+  const float2* Y;
+  double2* partial;        // [nsplit][chi*chi]
+  int chi;
+  int MMp, NNp;            // padded MMA M and N (floats)
+  unsigned outer, inner, CC;
+  int nsplit;
+  unsigned cols_per_split;
+  int cta_begin;
+};
+
+template <bool LAST>
+__global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* __restrict__ tasks, const int* __restrict__ cta_task) {
+  extern __shared__ __align__(1024) float smem[];
+  __shared__ uint32_t s_tmem;
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const TcGramTask t = tasks[cta_task[blockIdx.x]];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int split = blockIdx.x - t.cta_begin;
+  const int chi = t.chi;
+  // stage layout (floats): [A_hi | A_lo | B_hi | B_lo], A = MMp×KC, B = NNp×KC
+  const int a_floats = t.MMp * KC, b_floats = t.NNp * KC;
+  const int stage_floats = 2 * a_floats + 2 * b_floats;
+  int tmem_cols = 32;
+  while (tmem_cols < t.NNp) tmem_cols <<= 1;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[1])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // zero both stages once: padded rows / columns must read as zeros
+  for (int i = tid; i < 2 * stage_floats; i += TC_THREADS) smem[i] = 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem = s_tmem;
+  const uint32_t idesc = make_idesc(t.MMp, t.NNp, LAST ? 1 : 0, LAST ? 1 : 0);
+
+  const unsigned cb = (unsigned)split * t.cols_per_split;
+  const unsigned ce = min(t.CC, cb + t.cols_per_split);
+  constexpr int SCOLS = LAST ? 32 : 16;  // complex columns per stage (KC real K either way)
+  const int nstage = (int)((ce - cb + SCOLS - 1) / SCOLS);
+  uint32_t ph[2] = {0, 0};
+  int used[2] = {0, 0};
+
+  for (int st = 0; st < nstage; ++st) {
+    const int bsel = st & 1;
+    float* sA = smem + bsel * stage_floats;
+    float* sAl = sA + a_floats;
+    float* sBh = sAl + a_floats;
+    float* sBl = sBh + b_floats;
+    const unsigned k0 = cb + (unsigned)st * SCOLS;
+    if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }  // MMAs that read this stage are done
+    if (!LAST) {
+      // 16 complex columns of one outer slice: rows are 128-byte contiguous runs
+      const unsigned o = k0 / t.inner, n0 = k0 - o * t.inner;
+      const int nvalid = (int)min((unsigned)SCOLS, ce - k0);  // multiple of 2 by construction
+      for (int idx = tid; idx < ((chi + 7) & ~7) * 8; idx += TC_THREADS) {
+        const int row = (idx & 7) + 8 * (idx >> 6), q = (idx >> 3) & 7;  // row%8 fastest → conflict-free stores
+        if (row >= chi) continue;
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
+        if (2 * q < nvalid) {
+          const long long a = ((long long)o * chi + row) * t.inner + n0 + 2 * q;
+          y = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x = __ldg(reinterpret_cast<const float4*>(t.X + a));
+        }
+        float4 hi, lo;
+        split4(y, hi, lo);
+        const int m0 = 2 * row;  // Ycat rows (j,0) and (j,1)
+        int off = (m0 & 7) * 4 + q * 32 + (m0 >> 3) * 256;
+        *reinterpret_cast<float4*>(sA + off) = hi;
+        *reinterpret_cast<float4*>(sAl + off) = lo;
+        const float4 yr = make_float4(y.y, -y.x, y.w, -y.z);  // (Yi, −Yr)
+        split4(yr, hi, lo);
+        off += 4;  // row m0+1 (m0 even → same 8-row group)
+        *reinterpret_cast<float4*>(sA + off) = hi;
+        *reinterpret_cast<float4*>(sAl + off) = lo;
+        split4(x, hi, lo);
+        const int offb = (row & 7) * 4 + q * 32 + (row >> 3) * 256;
+        *reinterpret_cast<float4*>(sBh + offb) = hi;
+        *reinterpret_cast<float4*>(sBl + offb) = lo;
+      }
+    } else {
+      // 32 columns; each is a contiguous row of 2χ floats → MN-major SW128_32B tiles for both operands
+      const int w4 = chi >> 1;  // float4 per row (2χ floats)
+      const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
+      for (int idx = tid; idx < SCOLS * w4; idx += TC_THREADS) {
+        const int kl = idx / w4, l = idx - kl * w4;
+        const unsigned col = k0 + kl;
+        float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
+        if (col < ce) {
+          const long long a = (long long)col * chi + 2 * l;
+          y = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x = __ldg(reinterpret_cast<const float4*>(t.X + a));
+        }
+        const int r = kl & 3, ak = kl >> 2, am = l >> 3, c = (l & 7) >> 1, half = l & 1;
+        const int inatom = r * 128 + ((c ^ r) * 32) + half * 16;
+        float4 hi, lo;
+        split4(x, hi, lo);  // A = X (conjugated side: rows (i,ri))
+        int off = (am * 512 + ak * sboA + inatom) >> 2;
+        *reinterpret_cast<float4*>(sA + off) = hi;
+        *reinterpret_cast<float4*>(sAl + off) = lo;
+        split4(y, hi, lo);
+        off = (am * 512 + ak * sboB + inatom) >> 2;
+        *reinterpret_cast<float4*>(sBh + off) = hi;
+        *reinterpret_cast<float4*>(sBl + off) = lo;
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+      for (int term = 0; term < 3; ++term) {
+        const uint32_t a_base = smem_u32(term == 2 ? sAl : sA);
+        const uint32_t b_base = smem_u32(term == 1 ? sBl : sBh);
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ++ks) {
+          uint64_t ad, bd;
+          if (!LAST) {
+            ad = make_desc(a_base + ks * 256, 128, 1024, 0);
+            bd = make_desc(b_base + ks * 256, 128, 1024, 0);
+          } else {
+            const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
+            ad = make_desc(a_base + ks * 2 * sboA, 512, sboA, 1);
+            bd = make_desc(b_base + ks * 2 * sboB, 512, sboB, 1);
+          }
+          mma_tf32(tmem, ad, bd, idesc, (st | term | ks) != 0);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[bsel])) : "memory");
+    }
+    used[bsel] = 1;
+  }
+  // drain: wait for the last commit of each stage buffer (commits complete in issue order)
+  for (int bsel = 0; bsel < 2; ++bsel)
+    if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  // ---- epilogue (once per CTA): TMEM → partial sums -------------------------------------------------
+  double2* __restrict__ P = t.partial + (long long)split * chi * chi;
+  if (warp < 4) {
+    const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+    int m;  // row of D held by this lane
+    if (t.MMp == 128) m = warp * 32 + lane;
+    else m = (lane < 16) ? warp * 16 + lane : -1;  // M = 64: rows 16w..16w+15 live in lanes 0..15 of quadrant w
+    for (int n0 = 0; n0 < t.NNp; n0 += 16) {
+      uint32_t v[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                   : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                     "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                   : "r"(trow + n0));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (!LAST) {
+        // D[(j,part), i]: this lane holds row (j,part); columns i = n0..n0+15
+        if (m >= 0) {
+          const int j = m >> 1, part = m & 1;
+          if (j < chi) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int i = n0 + q;
+              if (i < chi) reinterpret_cast<double*>(&P[(long long)i * chi + j])[part] = (double)__uint_as_float(v[q]);
+            }
+          }
+        }
+      } else {
+        // D[(i,ri),(j,rj)]: even lane (i,0) makes re, odd lane (i,1) makes im
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float own = __uint_as_float(v[2 * q]);
+          const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * q + 1]), 1);
+          if (m >= 0) {
+            const int i = m >> 1, ri = m & 1, j = (n0 >> 1) + q;
+            if (i < chi && j < chi) {
+              const float val = ri ? (other - own) : (own + other);
+              reinterpret_cast<double*>(&P[(long long)i * chi + j])[ri] = (double)val;
+            }
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+}
+
 }  // namespace tc
 }  // namespace tnqs

@@ -157,6 +157,7 @@ typedef struct {
   double  mode_flops, gram_flops;     /* algorithmic real flops issued: 8·KK·MM·CC / 8·MM²·CC    */
   int64_t mode_launches, gram_launches;
   int64_t tc_launches;                /* launches of the tcgen05 (tensor-core) kernels             */
+  double  mode_bytes, gram_bytes;     /* algorithmic HBM bytes: tensors read + written once        */
 } tnqs_stats;
 int  tnqs_get_stats(tnqs_handle h, tnqs_stats* out, int reset);
 int  tnqs_set_profiling(tnqs_handle h, int on);

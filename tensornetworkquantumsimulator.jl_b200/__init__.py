@@ -11,3 +11,4 @@ from .api import (TensorNetworkState, BeliefPropagationCache, tensornetworkstate
                   random_tensornetworkstate, apply_gates, apply_circuit, update, expect, network,
                   maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays)
 from ._lib import TnqsError, LIB_PATH  # noqa: F401
+from .distributed import partition_vertices, cut_edges, shard  # noqa: F401

@@ -31,7 +31,8 @@ class Stats(C.Structure):
                 ("bp_messages", C.c_int64), ("two_site_gates", C.c_int64), ("bp_sweeps", C.c_int64),
                 ("mode_ms", C.c_double), ("gram_ms", C.c_double), ("small_ms", C.c_double),
                 ("mode_flops", C.c_double), ("gram_flops", C.c_double),
-                ("mode_launches", C.c_int64), ("gram_launches", C.c_int64), ("tc_launches", C.c_int64)]
+                ("mode_launches", C.c_int64), ("gram_launches", C.c_int64), ("tc_launches", C.c_int64),
+                ("mode_bytes", C.c_double), ("gram_bytes", C.c_double)]
 
 
 class TnqsError(RuntimeError):
@@ -79,7 +80,7 @@ def load():
         "tnqs_expect_local": [vp, C.c_int, i32p, dp, dp],
         "tnqs_expect_two_site": [vp, C.c_int, i32p, dp, dp],
         "tnqs_comm_unique_id": [vp],
-        "tnqs_comm_init": [vp, C.c_int, C.c_int, vp, i32p],
+        "tnqs_comm_init": [vp, C.c_int, C.c_int, C.c_char_p, i32p],
         "tnqs_get_stats": [vp, C.POINTER(Stats), C.c_int],
         "tnqs_set_profiling": [vp, C.c_int],
     }

@@ -148,8 +148,12 @@ class BeliefPropagationCache:
         """`Base.copy` (`beliefpropagationcache.jl:35-37`) — a device-to-device clone."""
         h = C.c_void_p()
         _lib.check(self._lib.tnqs_clone(self._h, C.byref(h)))
-        return BeliefPropagationCache(None, self.device, _handle=h, _graph=self.graph, _dtype=self.dtype,
-                                      _seq=self._seq)
+        out = BeliefPropagationCache(None, self.device, _handle=h, _graph=self.graph, _dtype=self.dtype,
+                                     _seq=self._seq)
+        for k in ("owner", "rank", "world"):
+            if hasattr(self, k):
+                setattr(out, k, getattr(self, k))
+        return out
 
     # -- accessors --------------------------------------------------------------------------------
     def set_edge_sequence(self, seq: Sequence[Tuple[Hashable, Hashable]]):
@@ -189,8 +193,18 @@ class BeliefPropagationCache:
         return out
 
     def network(self) -> TensorNetworkState:
-        """`network(ψ_bpc)` (`beliefpropagationcache.jl:24`): materialise the TNS on the host."""
-        return TensorNetworkState(self.graph, {v: self.site(v) for v in self.graph.vertices()}, self.dtype)
+        """`network(ψ_bpc)` (`beliefpropagationcache.jl:24`): materialise the TNS on the host.  On a
+        sharded cache every rank must call this (site tensors are broadcast from their owners)."""
+        owner = getattr(self, "owner", None)
+        if owner is None or getattr(self, "world", 1) == 1:
+            return TensorNetworkState(self.graph, {v: self.site(v) for v in self.graph.vertices()}, self.dtype)
+        import torch.distributed as dist
+        tensors = {}
+        for i, v in enumerate(self.graph.vertices()):
+            box = [self.site(v) if owner[i] == self.rank else None]
+            dist.broadcast_object_list(box, src=owner[i])
+            tensors[v] = box[0]
+        return TensorNetworkState(self.graph, tensors, self.dtype)
 
     def message(self, edge) -> np.ndarray:
         """`message(bpc, src => dst)` with the identity default (`abstractbeliefpropagationcache.jl:99-102`)."""

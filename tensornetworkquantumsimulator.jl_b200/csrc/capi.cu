@@ -140,14 +140,17 @@ int tnqs_expect_two_site(tnqs_handle h, int nobs, const int32_t* verts, const do
 
 int tnqs_comm_unique_id(void* out128) {
   return guarded([&] {
-    (void)out128;
-    throw Error(TNQS_EINVAL, "multi-GPU exchange is not built into this library version");
+    if (!out128) throw Error(TNQS_EINVAL, "null argument");
+    tnqs::NcclApi& api = tnqs::NcclApi::get();
+    tnqs::NcclUniqueId id;
+    api.check(api.GetUniqueId(&id), "ncclGetUniqueId");
+    std::memcpy(out128, &id, sizeof(id));
   });
 }
 int tnqs_comm_init(tnqs_handle h, int rank, int nranks, const void* unique_id128, const int32_t* owner) {
   return guarded([&] {
-    (void)h; (void)rank; (void)nranks; (void)unique_id128; (void)owner;
-    throw Error(TNQS_EINVAL, "multi-GPU exchange is not built into this library version");
+    if (!owner || (nranks > 1 && !unique_id128)) throw Error(TNQS_EINVAL, "null argument");
+    E(h).comm_init(rank, nranks, unique_id128, owner);
   });
 }
 

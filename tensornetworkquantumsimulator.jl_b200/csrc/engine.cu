@@ -82,6 +82,7 @@ Engine::Engine(const Engine& o)
       phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
   use_tc_ = o.use_tc_;
   profiling_ = o.profiling_;
+  comm_ = o.comm_; owner_ = o.owner_; rank_ = o.rank_; nranks_ = o.nranks_;
   TNQS_CUDA(cudaSetDevice(device_));
   TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   TNQS_CUDA(cudaEventCreate(&ev0_));
@@ -89,6 +90,7 @@ Engine::Engine(const Engine& o)
   TNQS_CUDA(cudaStreamSynchronize(o.stream_));
   site_.assign(nv_, nullptr);
   for (int v = 0; v < nv_; ++v) {
+    if (!o.site_[v]) continue;  // not owned by this rank
     const size_t b = (size_t)site_elems(v) * esz_;
     site_[v] = dalloc(b);
     TNQS_CUDA(cudaMemcpyAsync(site_[v], o.site_[v], b, cudaMemcpyDeviceToDevice, stream_));
@@ -254,6 +256,8 @@ void Engine::set_site(int v, const void* data, int ndim, const int64_t* shape) {
     sshape_[v][k] = (int)shape[1 + k];
   }
   dfree(site_[v]);
+  site_[v] = nullptr;
+  if (!owns(v)) return;  // shape bookkeeping only: the tensor lives on its owner
   const size_t b = (size_t)site_elems(v) * esz_;
   site_[v] = dalloc(b);
   TNQS_CUDA(cudaMemcpyAsync(site_[v], data, b, cudaMemcpyHostToDevice, stream_));
@@ -272,6 +276,7 @@ void Engine::get_site(int v, void* data, int64_t cap) {
   long long n = phys_[v];
   for (int x : sshape_[v]) n *= x;
   if (cap < n) throw Error(TNQS_ECAPACITY, "site buffer too small");
+  if (!owns(v) || !site_[v]) throw Error(TNQS_EINVAL, "site " + std::to_string(v) + " is owned by rank " + std::to_string(owner_.empty() ? 0 : owner_[v]));
   TNQS_CUDA(cudaSetDevice(device_));
   TNQS_CUDA(cudaMemcpyAsync(data, site_[v], (size_t)n * esz_, cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
@@ -317,6 +322,61 @@ void Engine::set_edge_sequence(const int32_t* seq, int n) {
 void Engine::get_stats(tnqs_stats* out, int reset) {
   *out = stats_;
   if (reset) stats_ = tnqs_stats{};
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU plumbing: every rank holds the graph, the bond dimensions and ALL
+// messages; site tensors live only on their owner.  What crosses NVLink is O(χ²) per edge:
+// the messages of a BP level and the reduced-factor Gram matrices of a gate batch.
+// ------------------------------------------------------------------------------------------------
+void Engine::comm_init(int rank, int nranks, const void* unique_id128, const int32_t* owner) {
+  if (nranks < 1 || rank < 0 || rank >= nranks) throw Error(TNQS_EINVAL, "bad rank / nranks");
+  TNQS_CUDA(cudaSetDevice(device_));
+  std::vector<int> own(owner, owner + nv_);
+  for (int v = 0; v < nv_; ++v)
+    if (own[v] < 0 || own[v] >= nranks) throw Error(TNQS_EINVAL, "owner rank out of range");
+  if (nranks > 1) {
+    NcclApi& api = NcclApi::get();
+    NcclUniqueId id;
+    std::memcpy(&id, unique_id128, sizeof(id));
+    auto h = std::make_shared<CommHandle>();
+    api.check(api.CommInitRank(&h->comm, nranks, id, rank), "ncclCommInitRank");
+    h->rank = rank; h->nranks = nranks;
+    comm_ = h;
+  }
+  rank_ = rank; nranks_ = nranks; owner_ = own;
+  for (int v = 0; v < nv_; ++v)
+    if (!owns(v) && site_[v]) { dfree(site_[v]); site_[v] = nullptr; }
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void Engine::exchange(const std::vector<Bcast>& items) {
+  if (nranks_ <= 1 || items.empty()) return;
+  NcclApi& api = NcclApi::get();
+  api.check(api.GroupStart(), "ncclGroupStart");
+  for (auto& b : items)
+    api.check(api.Broadcast(b.ptr, b.ptr, b.bytes, kNcclChar, b.root, comm_->comm, stream_), "ncclBroadcast");
+  api.check(api.GroupEnd(), "ncclGroupEnd");
+  stats_.kernel_launches += 1;
+}
+
+void Engine::allreduce_sum(double* dptr, size_t count) {
+  if (nranks_ <= 1 || count == 0) return;
+  NcclApi& api = NcclApi::get();
+  api.check(api.AllReduce(dptr, dptr, count, kNcclFloat64, kNcclSum, comm_->comm, stream_), "ncclAllReduce");
+}
+
+// scratch budget every rank agrees on (chunk boundaries of a gate batch carry a collective)
+size_t Engine::agreed_budget() {
+  double b = (double)scratch_budget();
+  if (nranks_ <= 1) return (size_t)b;
+  double* d = (double*)talloc(sizeof(double));
+  TNQS_CUDA(cudaMemcpyAsync(d, &b, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  NcclApi& api = NcclApi::get();
+  api.check(api.AllReduce(d, d, 1, kNcclFloat64, 3 /*ncclMin*/, comm_->comm, stream_), "ncclAllReduce(min)");
+  TNQS_CUDA(cudaMemcpyAsync(&b, d, sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  return (size_t)b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -451,6 +511,7 @@ std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks) {
 
 void Engine::launch_mode(std::vector<ModeTask>& tasks_in) {
   if (tasks_in.empty()) return;
+  for (auto& t : tasks_in) stats_.mode_bytes += (double)esz_ * ((double)t.KK + t.MM) * (double)t.CC;
   ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.mode_ms);
   std::vector<ModeTask> tasks = launch_mode_tc(tasks_in);
   if (tasks.empty()) return;
@@ -501,6 +562,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.gram_ms);
   std::vector<ReduceTask> red(tasks.size());
   std::vector<char> done(tasks.size(), 0);
+  for (auto& t : tasks) stats_.gram_bytes += (double)esz_ * 2.0 * t.MM * (double)t.CC;
   // ---- tcgen05 path: ComplexF32, fp32 accumulation (BP messages), one plane, χ ≤ 64 ------------------
   if (c64() && use_tc_ && !acc_double) {
     static bool attr_set = false;
@@ -655,6 +717,7 @@ void Engine::run_chains(std::vector<Chain>& chains) {
   std::vector<void*> bufA(chains.size(), nullptr), bufB(chains.size(), nullptr);
   for (size_t i = 0; i < chains.size(); ++i) {
     Chain& c = chains[i];
+    if (!owns(c.v)) { c.steps.clear(); c.result = nullptr; continue; }
     maxsteps = std::max(maxsteps, c.steps.size());
     c.result = site_[c.v];
     if (c.steps.empty()) continue;
@@ -713,7 +776,19 @@ std::vector<std::vector<int>> Engine::bp_levels(const std::vector<int>& seq) con
 }
 
 // one level: every item i is the update of message seq[i] (abstractbeliefpropagationcache.jl:162-190)
-void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& items, double* d_diff) {
+void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& all_items, double* d_diff) {
+  // staging buffers for every message of the level (all ranks), compute only what this rank owns
+  std::vector<int> items;
+  for (int it : all_items) {
+    const int de = dedge(seq[2 * it], seq[2 * it + 1]);
+    const int chi = bond_[de / 2];
+    if (!msg_next_[de] || msg_next_dim_[de] != chi) {
+      if (msg_next_[de]) dfree(msg_next_[de]);
+      msg_next_[de] = dalloc((size_t)chi * chi * esz_);
+      msg_next_dim_[de] = chi;
+    }
+    if (owns(seq[2 * it])) items.push_back(it);
+  }
   const size_t budget = scratch_budget();
   size_t pos = 0;
   while (pos < items.size()) {
@@ -752,11 +827,6 @@ void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& items
       gt[k] = gram_task(u, leg_pos(u, e), 1, site_[u], chains[k].result);
       const int chi = bond_[e];
       outs[k] = (double2*)talloc((size_t)chi * chi * sizeof(double2));
-      if (!msg_next_[de] || msg_next_dim_[de] != chi) {
-        if (msg_next_[de]) dfree(msg_next_[de]);
-        msg_next_[de] = dalloc((size_t)chi * chi * esz_);
-        msg_next_dim_[de] = chi;
-      }
       fin[k].g = outs[k]; fin[k].old_msg = msg_[de]; fin[k].new_msg = msg_next_[de];
       fin[k].diff = d_diff + it; fin[k].chi = chi;
     }
@@ -771,7 +841,15 @@ void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& items
     free_temps();
     pos = end;
   }
-  for (int it : items) {  // commit the level
+  if (nranks_ > 1) {  // the level's new messages travel from the owner of their source vertex
+    std::vector<Bcast> bc;
+    for (int it : all_items) {
+      const int de = dedge(seq[2 * it], seq[2 * it + 1]);
+      bc.push_back({msg_next_[de], (size_t)msg_next_dim_[de] * msg_next_dim_[de] * esz_, owner_[seq[2 * it]]});
+    }
+    exchange(bc);
+  }
+  for (int it : all_items) {  // commit the level
     const int de = dedge(seq[2 * it], seq[2 * it + 1]);
     std::swap(msg_[de], msg_next_[de]);
     std::swap(msg_dim_[de], msg_next_dim_[de]);
@@ -810,9 +888,11 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
   double* d_diff = (double*)dalloc(sizeof(double) * nseq);
   std::vector<double> h_diff(nseq);
   for (int it = 1; it <= maxiter; ++it) {
+    if (nranks_ > 1) TNQS_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(double) * nseq, stream_));
     for (auto& lv : levels) bp_level(seq, lv, d_diff);
     stats_.bp_sweeps += 1;
     if (use_tol) {
+      allreduce_sum(d_diff, nseq);
       TNQS_CUDA(cudaMemcpyAsync(h_diff.data(), d_diff, sizeof(double) * nseq, cudaMemcpyDeviceToHost, stream_));
       TNQS_CUDA(cudaStreamSynchronize(stream_));
       double s = 0;
@@ -869,6 +949,7 @@ void Engine::apply_one_site_batch(const std::vector<std::pair<int, std::vector<c
   for (size_t i = 0; i < g.size(); ++i) {
     const int v = g[i].first;
     const int d = phys_[v];
+    if (!owns(v)) { t[i].data = nullptr; t[i].plane = 0; t[i].d = d; continue; }
     t[i].data = site_[v];
     t[i].plane = site_elems(v) / d;
     t[i].d = d;
@@ -898,7 +979,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
   const double eps = c64() ? 1.1920928955078125e-07 : 2.220446049250313e-16;
   const double sqrt_cutoff = ao.sqrt_cutoff >= 0 ? ao.sqrt_cutoff : 10 * eps;  // simple_update.jl:32-33
   const bool normalize = ao.normalize_tensors != 0;
-  const size_t budget = scratch_budget();
+  const size_t budget = agreed_budget();
   size_t gpos = 0;
   while (gpos < gate_ids.size()) {
     size_t gend = gpos, bytes = 0;
@@ -919,6 +1000,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       const int g = gate_ids[gpos + k];
       for (int s = 0; s < 2; ++s) {
         const int v = verts[2 * g + s], o = verts[2 * g + 1 - s];
+        if (!owns(v)) continue;  // the owner of the site gauges it
         for (size_t p = 0; p < inc_[v].size(); ++p) {
           const int w = inc_[v][p].nbr;
           if (w == o) continue;
@@ -985,7 +1067,21 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         G[2 * k + s] = (double2*)talloc((size_t)nn[2 * k + s] * nn[2 * k + s] * sizeof(double2));
       }
     }
-    launch_gram(gt, /*acc_double=*/true, G, /*transpose=*/false);
+    {
+      // each rank forms the Gram matrices of the sites it owns; every rank then receives all of them
+      // and repeats the (deterministic) O(χ³) algebra, so bond dimensions, singular values and
+      // messages stay replicated without a second exchange
+      std::vector<GramTask> gto;
+      std::vector<double2*> Go;
+      std::vector<Bcast> bc;
+      for (int i = 0; i < 2 * ng; ++i) {
+        const int v = verts[2 * gate_ids[gpos + i / 2] + (i & 1)];
+        if (owns(v)) { gto.push_back(gt[i]); Go.push_back(G[i]); }
+        if (nranks_ > 1) bc.push_back({G[i], (size_t)nn[i] * nn[i] * sizeof(double2), owner_[v]});
+      }
+      launch_gram(gto, /*acc_double=*/true, Go, /*transpose=*/false);
+      exchange(bc);
+    }
 
     // ---- 4. eig(G), θ, SVD(θ), truncation ------------------------------------------------------
     std::vector<SuGateTask> st(ng);
@@ -1082,15 +1178,17 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       for (auto& en : envs)
         if (!flags[2 * en.task]) proj[2 * en.gate + en.site].steps.push_back({en.pos, mt[en.task].proj});
       run_chains(proj);
-      std::vector<ModeTask> fin(2 * ng);
-      std::vector<void*> newbuf(2 * ng);
+      std::vector<ModeTask> fin;
+      std::vector<void*> newbuf(2 * ng, nullptr);
       for (int k = 0; k < ng; ++k) {
         const int g = gate_ids[gpos + k];
         for (int s = 0; s < 2; ++s) {
           const int v = verts[2 * g + s];
+          if (!owns(v)) continue;
           const int d = phys_[v];
           const int pos = epos[2 * k + s];
-          ModeTask& t = fin[2 * k + s];
+          fin.emplace_back();
+          ModeTask& t = fin.back();
           t = ModeTask{};
           int chi;
           leg_view(v, pos, &t.outer, &chi, &t.inner);
@@ -1116,9 +1214,10 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         bond_[e] = keep[k];
         for (int s = 0; s < 2; ++s) {
           const int v = verts[2 * g + s];
+          sshape_[v][epos[2 * k + s]] = keep[k];
+          if (!owns(v)) continue;
           dfree(site_[v]);
           site_[v] = newbuf[2 * k + s];
-          sshape_[v][epos[2 * k + s]] = keep[k];
           touched.push_back(v);
         }
         for (int de = 2 * e; de < 2 * e + 2; ++de) {
@@ -1289,11 +1388,19 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
   std::vector<size_t> offs(nobs);
   for (int i = 0; i < nobs; ++i) { offs[i] = tot; tot += (size_t)phys_[verts[i]] * phys_[verts[i]]; }
   double2* d_rho = (double2*)talloc(tot * sizeof(double2));
-  for (int i = 0; i < nobs; ++i) {
-    gt[i] = gram_task(verts[i], -1, 1, site_[verts[i]], chains[i].result);
-    outs[i] = d_rho + offs[i];
+  TNQS_CUDA(cudaMemsetAsync(d_rho, 0, tot * sizeof(double2), stream_));
+  {
+    std::vector<GramTask> gto;
+    std::vector<double2*> oo;
+    for (int i = 0; i < nobs; ++i) {
+      outs[i] = d_rho + offs[i];
+      if (!owns(verts[i])) continue;  // the owner contracts; the others contribute zeros to the sum
+      gto.push_back(gram_task(verts[i], -1, 1, site_[verts[i]], chains[i].result));
+      oo.push_back(outs[i]);
+    }
+    launch_gram(gto, true, oo, /*transpose=*/true);  // buffer[s*d+s'] = ρ[s][s']
+    allreduce_sum(reinterpret_cast<double*>(d_rho), 2 * tot);
   }
-  launch_gram(gt, true, outs, /*transpose=*/true);  // buffer[s*d+s'] = ρ[s][s']
   std::vector<cplx> rho(tot);
   TNQS_CUDA(cudaMemcpyAsync(rho.data(), d_rho, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
@@ -1349,8 +1456,19 @@ void Engine::expect_two_site(int nobs, const int32_t* verts, const double* ops, 
     tot += (size_t)gt[i].MM * gt[i].MM;
   }
   double2* d_e = (double2*)talloc(tot * sizeof(double2));
-  for (int i = 0; i < 2 * nobs; ++i) outs[i] = d_e + offs[i];
-  launch_gram(gt, true, outs, /*transpose=*/false);  // buffer[(s'b')*n + (s b)] = E[s,b,s',b']
+  TNQS_CUDA(cudaMemsetAsync(d_e, 0, tot * sizeof(double2), stream_));
+  {
+    std::vector<GramTask> gto;
+    std::vector<double2*> oo;
+    for (int i = 0; i < 2 * nobs; ++i) {
+      outs[i] = d_e + offs[i];
+      if (!owns(chains[i].v)) continue;
+      gto.push_back(gt[i]);
+      oo.push_back(outs[i]);
+    }
+    launch_gram(gto, true, oo, /*transpose=*/false);  // buffer[(s'b')*n + (s b)] = E[s,b,s',b']
+    allreduce_sum(reinterpret_cast<double*>(d_e), 2 * tot);
+  }
   std::vector<cplx> E(tot);
   TNQS_CUDA(cudaMemcpyAsync(E.data(), d_e, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));

@@ -33,6 +33,10 @@ struct Error : std::runtime_error {
       throw ::tnqs::Error(TNQS_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));        \
   } while (0)
 
+}  // namespace tnqs
+#include "comm.cuh"
+namespace tnqs {
+
 struct Leg {
   int edge, nbr;
 };
@@ -69,6 +73,10 @@ class Engine {
   void expect_local(int nobs, const int32_t* verts, const double* ops, double* out);
   void expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out);
 
+  // multi-GPU: vertex ownership + NCCL exchange of the replicated small data (messages, Gram matrices)
+  void comm_init(int rank, int nranks, const void* unique_id128, const int32_t* owner);
+  bool owns(int v) const { return owner_.empty() || owner_[v] == rank_; }
+
   void get_stats(tnqs_stats* out, int reset);
   void set_profiling(int on) { profiling_ = on != 0; }
 
@@ -98,6 +106,13 @@ class Engine {
   tnqs_stats stats_{};
   bool profiling_ = false;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
+  std::shared_ptr<CommHandle> comm_;  // null: single GPU
+  std::vector<int> owner_;            // owner rank per vertex (empty: everything local)
+  int rank_ = 0, nranks_ = 1;
+  struct Bcast { void* ptr; size_t bytes; int root; };
+  void exchange(const std::vector<Bcast>& items);       // grouped broadcasts on the engine stream
+  void allreduce_sum(double* dptr, size_t count);
+  size_t agreed_budget();
 
   // ---- helpers -------------------------------------------------------------------------------
   void* dalloc(size_t bytes);

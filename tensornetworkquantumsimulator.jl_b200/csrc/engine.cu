@@ -472,8 +472,10 @@ std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks) {
     k.ntiles = (int)((t.CC + cols - 1) / cols);
     const int g = last ? 1 : 0;
     tt[g].push_back(k);
-    const size_t out_bytes = last ? (size_t)128 * (NNp + 4) * 4 : (size_t)(NNp / 2) * 128 * 4;
-    smem_max[g] = std::max(smem_max[g], ((b_bytes / 4 + 255) & ~size_t(255)) * 4 + 2 * 128 * tc::KC * 4 + out_bytes);
+    // output staging aliases the A stage (2·128·KC floats = 32 KB ≥ 128·NNp·4 for NNp ≤ 64; larger N adds the rest)
+    const size_t out_bytes = last ? (size_t)128 * NNp * 4 : (size_t)(NNp / 2) * 128 * 4;
+    const size_t a_bytes = std::max<size_t>((size_t)2 * 128 * tc::KC * 4, out_bytes);
+    smem_max[g] = std::max(smem_max[g], ((b_bytes / 4 + 255) & ~size_t(255)) * 4 + a_bytes);
     flops += 8.0 * t.KK * t.MM * (double)t.CC;
   }
   if (tt[0].empty() && tt[1].empty()) return rest;

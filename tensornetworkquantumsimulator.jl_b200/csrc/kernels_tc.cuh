@@ -219,7 +219,10 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
   float* sB = smem;
   float* sAh = smem + ((b_floats + 255) & ~255);  // 1024-byte aligned: the swizzle is address based
   float* sAl = sAh + 128 * KC;
-  float* sOut = sAl + 128 * KC;                   // MID: [NNp/2][128] floats, LAST: [128][NNp+4] floats
+  // The output staging tile aliases the A stage: once the tile's MMAs have completed the stage is dead
+  // (the next tile waits in registers).  MID: [NNp/2][128] floats; LAST: [128][NNp] floats with the
+  // float4 column XOR-swizzled by (row & 7) to keep the row-per-lane stores conflict free.
+  float* sOut = sAh;
   int tmem_cols = 32;
   while (tmem_cols < t.NNp) tmem_cols <<= 1;
 
@@ -295,6 +298,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
     asm volatile("tcgen05.fence::after_thread_sync;");
     // ---- epilogue: TMEM → registers → staging tile → coalesced global stores ---------------------
     const int quad = warp & 3, half = warp >> 2;
+    // XOR swizzle of the staging tile's float4 columns: stay inside an aligned power-of-two group
+    const int nf4 = t.NNp >> 2;
+    const int swmask = min(7, (nf4 & -nf4) - 1);
     const uint32_t trow = tmem + ((uint32_t)(quad * 32) << 16);
     const int nhalf = (t.NNp / 16 + 1) / 2;  // 16-column groups handled by half 0
     const int g0 = half ? nhalf : 0, g1 = half ? t.NNp / 16 : nhalf;
@@ -317,7 +323,8 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
       }
     } else {
       const int row = quad * 32 + lane;
-      float* dst = sOut + row * (t.NNp + 4);
+      float* dst = sOut + row * t.NNp;
+      const int sw = row & swmask;
       for (int g = g0; g < g1; ++g) {
         uint32_t v[16];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -330,7 +337,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
           float4 y;
           y.x = __uint_as_float(v[4 * q]); y.y = __uint_as_float(v[4 * q + 1]);
           y.z = __uint_as_float(v[4 * q + 2]); y.w = __uint_as_float(v[4 * q + 3]);
-          *reinterpret_cast<float4*>(dst + g * 16 + q * 4) = y;
+          *reinterpret_cast<float4*>(dst + (((g * 4 + q) ^ sw) << 2)) = y;
         }
       }
     }
@@ -359,7 +366,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
           const int row = idx / w4, q = idx - row * w4;
           const unsigned col = c0 + row;
           if (col < t.CC) {
-            const float4 y = *reinterpret_cast<const float4*>(sOut + row * (t.NNp + 4) + 4 * q);
+            const float4 y = *reinterpret_cast<const float4*>(sOut + row * t.NNp + ((q ^ (row & swmask)) << 2));
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(t.out + (long long)col * t.chi_out) + 4 * q) = y;
           }
         }
@@ -370,15 +377,16 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
           if (col < t.CC) {
             const int pp = jp / t.chi_out, c = jp - pp * t.chi_out;
             float2 y;
-            y.x = sOut[row * (t.NNp + 4) + 2 * jp];
-            y.y = sOut[row * (t.NNp + 4) + 2 * jp + 1];
+            const int f = 2 * jp;
+            const float* src = sOut + row * t.NNp + ((((f >> 2) ^ (row & swmask)) << 2) | (f & 3));
+            y.x = src[0];
+            y.y = src[1];
             t.out[pp * t.ops + (long long)col * t.chi_out + c] = y;
           }
         }
       }
     }
-    // the next iteration's stage writes touch sAh/sAl only; sOut is rewritten after the next MMA wait,
-    // which every thread reaches only after passing the __syncthreads() that follows the stage writes
+    __syncthreads();  // copy-out done: the staging tile (= A stage) may be overwritten by the next tile
   }
   if (!b_ready) mbar_wait(smem_u32(&s_bar_b), 0);  // never leave a bulk copy in flight
   __syncthreads();

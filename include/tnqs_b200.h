@@ -158,6 +158,8 @@ typedef struct {
   int64_t mode_launches, gram_launches;
   int64_t tc_launches;                /* launches of the tcgen05 (tensor-core) kernels             */
   double  mode_bytes, gram_bytes;     /* algorithmic HBM bytes: tensors read + written once        */
+  double  wall_ms;                    /* host wall time spent inside tnqs_apply_gates / tnqs_bp_update
+                                         (device time bp_ms + su_ms below it means the host is the limit) */
 } tnqs_stats;
 int  tnqs_get_stats(tnqs_handle h, tnqs_stats* out, int reset);
 int  tnqs_set_profiling(tnqs_handle h, int on);

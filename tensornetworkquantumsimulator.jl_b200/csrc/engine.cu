@@ -1,6 +1,8 @@
 // engine.cu — implementation of the host-side engine (see engine.cuh).
 #include "engine.cuh"
 
+#include <chrono>
+#include <functional>
 #include <cstdio>
 #include <numeric>
 #include <set>
@@ -10,6 +12,31 @@
 namespace tnqs {
 
 using cplx = std::complex<double>;
+
+// Process-wide free list of upload chunks per device: apply_gates / update clone the engine for the
+// reference's functional-copy semantics, and pinning host memory (cudaHostAlloc) costs milliseconds.
+namespace {
+struct UpPool {
+  std::mutex mu;
+  std::map<int, std::vector<std::pair<char*, char*>>> free_;
+  static UpPool& get() { static UpPool p; return p; }
+  std::pair<char*, char*> take(int device, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto& v = free_[device];
+      if (!v.empty()) { auto c = v.back(); v.pop_back(); return c; }
+    }
+    char *d = nullptr, *h = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) throw Error(TNQS_ECUDA, "cudaMalloc(upload chunk) failed");
+    if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaFree(d); throw Error(TNQS_ECUDA, "cudaHostAlloc(upload chunk) failed"); }
+    return {d, h};
+  }
+  void give(int device, char* d, char* h) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_[device].push_back({d, h});
+  }
+};
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // construction / destruction
@@ -114,6 +141,11 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : temps_) cudaFreeAsync(p, stream_);
   for (char* p : arena_) cudaFreeAsync(p, stream_);
+  for (auto& s : up_) {  // the stream is idle: the chunks can serve another engine
+    for (auto& c : s.chunks) UpPool::get().give(device_, c.dev, c.host);
+    s.chunks.clear();
+    if (s.done) cudaEventDestroy(s.done);
+  }
   for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
@@ -159,11 +191,44 @@ void Engine::free_temps() {
   temps_.clear();
   arena_cur_ = 0;  // chunks stay cached; reuse is ordered by the single engine stream
   arena_off_ = 0;
+  // close the upload epoch: its pinned mirrors may be rewritten only after the copies queued so far ran
+  UpSet& s = up_[up_cur_];
+  if (s.cur != 0 || s.off != 0) {
+    if (!s.done) TNQS_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    TNQS_CUDA(cudaEventRecord(s.done, stream_));
+    s.pending = true;
+    up_cur_ = (up_cur_ + 1) % kUpSets;
+    UpSet& n = up_[up_cur_];
+    if (n.pending) { TNQS_CUDA(cudaEventSynchronize(n.done)); n.pending = false; }
+    n.cur = 0; n.off = 0;
+  }
+}
+// device block + its pinned host mirror from the current upload set
+void* Engine::up_alloc(size_t bytes, void** host) {
+  bytes = (bytes + 255) & ~size_t(255);
+  if (bytes == 0) bytes = 256;
+  if (bytes > kUpChunk) { *host = nullptr; return talloc(bytes); }  // oversized table: plain (synchronising) copy
+  UpSet& s = up_[up_cur_];
+  if (s.cur >= s.chunks.size() || s.off + bytes > kUpChunk) {
+    if (s.cur < s.chunks.size() && s.off > 0) ++s.cur;
+    if (s.cur >= s.chunks.size()) {
+      auto c = UpPool::get().take(device_, kUpChunk);
+      s.chunks.push_back({c.first, c.second});
+    }
+    s.off = 0;
+  }
+  *host = s.chunks[s.cur].host + s.off;
+  void* d = s.chunks[s.cur].dev + s.off;
+  s.off += bytes;
+  return d;
 }
 template <class T> T* Engine::upload(const std::vector<T>& v) {
-  T* d = (T*)talloc(v.size() * sizeof(T));
-  if (!v.empty())
-    TNQS_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream_));
+  void* h = nullptr;
+  T* d = (T*)up_alloc(v.size() * sizeof(T), &h);
+  if (v.empty()) return d;
+  const void* src = v.data();
+  if (h) { std::memcpy(h, v.data(), v.size() * sizeof(T)); src = h; }
+  TNQS_CUDA(cudaMemcpyAsync(d, src, v.size() * sizeof(T), cudaMemcpyHostToDevice, stream_));
   return d;
 }
 int Engine::dedge(int src, int dst) const {
@@ -569,8 +634,11 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   if (c64() && use_tc_ && !acc_double) {
     static bool attr_set = false;
     if (!attr_set) {
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_set = true;
     }
     std::vector<tc::TcGramTask> tt[2];
@@ -622,8 +690,16 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       }
       tc::TcGramTask* dt = upload(tt[g]);
       int* dc = upload(cta_task);
-      if (g == 0) tc::tc_gram_kernel<false><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
-      else tc::tc_gram_kernel<true><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+      int maxchi = 0;
+      for (auto& t : tt[g]) maxchi = std::max(maxchi, t.chi);
+      if (g == 0) {
+        if (maxchi <= 32) tc::tc_gram_kernel<false, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<false, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+      } else {
+        if (maxchi <= 16) tc::tc_gram_kernel<true, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else if (maxchi <= 32) tc::tc_gram_kernel<true, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<true, 4, 1><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+      }
       count_launch();
       stats_.gram_launches += 1;
       stats_.tc_launches += 1;
@@ -791,42 +867,99 @@ void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& all_i
     }
     if (owns(seq[2 * it])) items.push_back(it);
   }
+  // Messages leaving the same vertex share partial products: with the legs split recursively in
+  // halves, the branch towards one half first absorbs every message of the other half, so a degree-4
+  // vertex sending on all legs costs 8 mode products instead of 4·3 (degree 6: 16 instead of 30).
+  struct Group { int u; std::vector<int> its; };
+  std::vector<Group> groups;
+  {
+    std::map<int, int> gidx;
+    for (int it : items) {
+      const int u = seq[2 * it];
+      auto f = gidx.find(u);
+      if (f == gidx.end()) { f = gidx.emplace(u, (int)groups.size()).first; groups.push_back({u, {}}); }
+      groups[f->second].its.push_back(it);
+    }
+  }
+  struct Node { int v, pos; const void* mat; int in; void* out; int level; };
+  std::vector<Node> nodes;
+  std::vector<int> leaf;  // per leg position of the current vertex: node id holding the result (−1: the site tensor)
+  std::vector<char> want, isset;
+  std::vector<const void*> lmat;
+  // cur = node that has absorbed every set leg outside L; returns nothing, fills leaf[]
+  std::function<void(const std::vector<int>&, int, int, int)> build = [&](const std::vector<int>& L, int cur, int level, int u) {
+    bool any = false;
+    for (int p : L) any |= want[p] != 0;
+    if (!any) return;
+    if (L.size() == 1) { leaf[L[0]] = cur; return; }
+    const size_t h = L.size() / 2;
+    const std::vector<int> L1(L.begin(), L.begin() + h), L2(L.begin() + h, L.end());
+    for (int side = 0; side < 2; ++side) {
+      const std::vector<int>& keep = side == 0 ? L1 : L2;
+      const std::vector<int>& absorb = side == 0 ? L2 : L1;
+      bool w = false;
+      for (int p : keep) w |= want[p] != 0;
+      if (!w) continue;
+      int x = cur, lv = level;
+      for (int p : absorb) {
+        if (!isset[p]) continue;  // identity default: nothing to absorb
+        nodes.push_back({u, p, lmat[p], x, nullptr, lv});
+        x = (int)nodes.size() - 1;
+        ++lv;
+      }
+      build(keep, x, lv, u);
+    }
+  };
+  auto plan_group = [&](const Group& g, std::vector<std::pair<int, int>>& results /* (item, node) */) {
+    const int u = g.u, z = (int)inc_[u].size();
+    want.assign(z, 0); isset.assign(z, 0); lmat.assign(z, nullptr); leaf.assign(z, -1);
+    for (int p = 0; p < z; ++p) {
+      const int de = dedge(inc_[u][p].nbr, u);
+      isset[p] = msg_set_[de] ? 1 : 0;
+      lmat[p] = msg_[de];
+    }
+    std::vector<int> legs(z);
+    for (int p = 0; p < z; ++p) legs[p] = p;
+    for (int it : g.its) want[leg_pos(u, dedge(u, seq[2 * it + 1]) / 2)] = 1;
+    build(legs, -1, 0, u);
+    for (int it : g.its) results.push_back({it, leaf[leg_pos(u, dedge(u, seq[2 * it + 1]) / 2)]});
+  };
   const size_t budget = scratch_budget();
   size_t pos = 0;
-  while (pos < items.size()) {
-    // chunk by scratch
+  while (pos < groups.size()) {
+    // chunk by scratch: one buffer per product node
+    nodes.clear();
+    std::vector<std::pair<int, int>> results;
     size_t end = pos, bytes = 0;
-    while (end < items.size()) {
-      const int u = seq[2 * items[end]];
-      const size_t need = (inc_[u].size() > 1 ? 2 : 0) * (size_t)site_elems(u) * esz_;
-      if (end > pos && bytes + need > budget) break;
+    while (end < groups.size()) {
+      const size_t n0 = nodes.size(), r0 = results.size();
+      plan_group(groups[end], results);
+      const size_t need = (nodes.size() - n0) * (size_t)site_elems(groups[end].u) * esz_;
+      if (end > pos && bytes + need > budget) { nodes.resize(n0); results.resize(r0); break; }
       bytes += need;
       ++end;
     }
-    const int n = (int)(end - pos);
-    std::vector<Chain> chains(n);
-    for (int k = 0; k < n; ++k) {
-      const int it = items[pos + k];
-      const int u = seq[2 * it], v = seq[2 * it + 1];
-      chains[k].v = u;
-      for (size_t p = 0; p < inc_[u].size(); ++p) {
-        const int w = inc_[u][p].nbr;
-        if (w == v) continue;
-        const int de = dedge(w, u);
-        if (!msg_set_[de]) continue;  // identity default: nothing to absorb
-        chains[k].steps.push_back({(int)p, msg_[de]});
-      }
+    int maxlevel = -1;
+    for (auto& nd : nodes) {
+      nd.out = talloc((size_t)site_elems(nd.v) * esz_);
+      maxlevel = std::max(maxlevel, nd.level);
     }
-    run_chains(chains);
+    for (int lv = 0; lv <= maxlevel; ++lv) {
+      std::vector<ModeTask> tasks;
+      for (auto& nd : nodes)
+        if (nd.level == lv) tasks.push_back(mode_task(nd.v, nd.pos, nd.in < 0 ? site_[nd.v] : nodes[nd.in].out, nd.out, nd.mat));
+      launch_mode(tasks);
+    }
+    const int n = (int)results.size();
     std::vector<GramTask> gt(n);
     std::vector<double2*> outs(n);
     std::vector<BpFinTask> fin(n);
     for (int k = 0; k < n; ++k) {
-      const int it = items[pos + k];
+      const int it = results[k].first;
       const int u = seq[2 * it], v = seq[2 * it + 1];
       const int de = dedge(u, v);
       const int e = de / 2;
-      gt[k] = gram_task(u, leg_pos(u, e), 1, site_[u], chains[k].result);
+      gt[k] = gram_task(u, leg_pos(u, e), 1, site_[u], results[k].second < 0 ? site_[u] : nodes[results[k].second].out);
       const int chi = bond_[e];
       outs[k] = (double2*)talloc((size_t)chi * chi * sizeof(double2));
       fin[k].g = outs[k]; fin[k].old_msg = msg_[de]; fin[k].new_msg = msg_next_[de];
@@ -860,7 +993,18 @@ void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& all_i
   stats_.bp_messages += (int64_t)items.size();
 }
 
+namespace {
+struct WallScope {  // host wall time of the outermost hot-path call
+  double* acc; int* depth; std::chrono::steady_clock::time_point t0;
+  WallScope(double* a, int* d) : acc(a), depth(d), t0(std::chrono::steady_clock::now()) { ++*depth; }
+  ~WallScope() {
+    if (--*depth == 0) *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+};
+}  // namespace
+
 tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
+  WallScope ws(&stats_.wall_ms, &wall_depth_);
   TNQS_CUDA(cudaSetDevice(device_));
   check_shapes();
   std::vector<int> seq;
@@ -1253,6 +1397,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
 void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts, const double* mats,
                          const tnqs_apply_opts* aop, const tnqs_bp_opts* bo, int update_cache,
                          double* errs, tnqs_bp_report* reports, int max_reports, int* n_reports) {
+  WallScope ws(&stats_.wall_ms, &wall_depth_);
   TNQS_CUDA(cudaSetDevice(device_));
   check_shapes();
   tnqs_apply_opts ao{0, 1, -1.0, 1, -1.0};

@@ -9,6 +9,8 @@
 #include <complex>
 #include <cstring>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -103,8 +105,20 @@ class Engine {
   std::vector<void*> temps_;    // stream-ordered temporaries freed by free_temps()
   std::vector<char*> arena_;    // cached chunks for small temporaries
   size_t arena_cur_ = 0, arena_off_ = 0;
+  // Task tables go host→device through a ring of (device, pinned-host mirror) chunks so that the
+  // copies are truly asynchronous (a pageable cudaMemcpyAsync above 64 KB drains the stream first and
+  // would serialise host preparation with device execution).  One set per free_temps() epoch; a set is
+  // reused only after the event recorded at the end of its previous epoch has completed.
+  struct UpChunk { char* dev; char* host; };
+  struct UpSet { std::vector<UpChunk> chunks; size_t cur = 0, off = 0; cudaEvent_t done = nullptr; bool pending = false; };
+  static constexpr int kUpSets = 4;
+  static constexpr size_t kUpChunk = 4ull << 20;
+  UpSet up_[kUpSets];
+  int up_cur_ = 0;
+  void* up_alloc(size_t bytes, void** host);
   tnqs_stats stats_{};
   bool profiling_ = false;
+  int wall_depth_ = 0;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
   std::shared_ptr<CommHandle> comm_;  // null: single GPU
   std::vector<int> owner_;            // owner rank per vertex (empty: everything local)

@@ -417,7 +417,9 @@ struct TcGramTask {
   int cta_begin;
 };
 
-template <bool LAST>
+// NIT = (X,Y) float4 pairs a thread stages per K step, PD = how many K steps ahead the global loads
+// run (register prefetch ring): the DRAM latency of step st+PD overlaps the split / MMA of step st.
+template <bool LAST, int NIT, int PD>
 __global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* __restrict__ tasks, const int* __restrict__ cta_task) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint32_t s_tmem;
@@ -455,94 +457,130 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* _
   uint32_t ph[2] = {0, 0};
   int used[2] = {0, 0};
 
-  for (int st = 0; st < nstage; ++st) {
-    const int bsel = st & 1;
-    float* sA = smem + bsel * stage_floats;
-    float* sAl = sA + a_floats;
-    float* sBh = sAl + a_floats;
-    float* sBl = sBh + b_floats;
-    const unsigned k0 = cb + (unsigned)st * SCOLS;
-    if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }  // MMAs that read this stage are done
+  // ---- per-thread constants of the staging pattern ----------------------------------------------------
+  // MID : item (row, q): row = (idx&7) + 8·(idx>>6), q = (idx>>3)&7 (row%8 fastest → conflict-free stores);
+  //       global element offset inside an outer slice: row·inner + 2q
+  // LAST: item (kl, l): column kl of the stage, float4 l of its 2χ-float row
+  int it_row[NIT], it_q[NIT];       // MID: row, q        LAST: kl, l
+  int offA[NIT], offB[NIT];         // shared-memory float offsets
+  bool it_ok[NIT];
+  const int w4 = chi >> 1;
+  const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
+#pragma unroll
+  for (int j = 0; j < NIT; ++j) {
+    const int idx = tid + j * TC_THREADS;
     if (!LAST) {
-      // 16 complex columns of one outer slice: rows are 128-byte contiguous runs
+      const int row = (idx & 7) + 8 * (idx >> 6), q = (idx >> 3) & 7;
+      it_row[j] = row; it_q[j] = q; it_ok[j] = row < chi;
+      const int m0 = 2 * row;  // Ycat rows (j,0) and (j,1)
+      offA[j] = (m0 & 7) * 4 + q * 32 + (m0 >> 3) * 256;
+      offB[j] = (row & 7) * 4 + q * 32 + (row >> 3) * 256;
+    } else {
+      const int kl = idx / w4, l = idx - kl * w4;
+      it_row[j] = kl; it_q[j] = l; it_ok[j] = kl < SCOLS;
+      const int r = kl & 3, ak = kl >> 2, am = l >> 3, c = (l & 7) >> 1, half = l & 1;
+      const int inatom = r * 128 + ((c ^ r) * 32) + half * 16;
+      offA[j] = (am * 512 + ak * sboA + inatom) >> 2;
+      offB[j] = (am * 512 + ak * sboB + inatom) >> 2;
+    }
+  }
+
+  float4 rx[PD][NIT], ry[PD][NIT];
+  auto load_stage = [&](int st, float4 (&x)[NIT], float4 (&y)[NIT]) {
+    const unsigned k0 = cb + (unsigned)st * SCOLS;
+    if (!LAST) {
+      // 16 complex columns of one outer slice (inner % 16 == 0 and the split starts on a multiple of 16)
       const unsigned o = k0 / t.inner, n0 = k0 - o * t.inner;
       const int nvalid = (int)min((unsigned)SCOLS, ce - k0);  // multiple of 2 by construction
-      for (int idx = tid; idx < ((chi + 7) & ~7) * 8; idx += TC_THREADS) {
-        const int row = (idx & 7) + 8 * (idx >> 6), q = (idx >> 3) & 7;  // row%8 fastest → conflict-free stores
-        if (row >= chi) continue;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
-        if (2 * q < nvalid) {
-          const long long a = ((long long)o * chi + row) * t.inner + n0 + 2 * q;
-          y = __ldg(reinterpret_cast<const float4*>(t.Y + a));
-          x = __ldg(reinterpret_cast<const float4*>(t.X + a));
+      const long long base = (long long)o * chi * t.inner + n0;
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
+        if (it_ok[j] && 2 * it_q[j] < nvalid) {
+          const long long a = base + (long long)it_row[j] * t.inner + 2 * it_q[j];
+          y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
         }
-        float4 hi, lo;
-        split4(y, hi, lo);
-        const int m0 = 2 * row;  // Ycat rows (j,0) and (j,1)
-        int off = (m0 & 7) * 4 + q * 32 + (m0 >> 3) * 256;
-        *reinterpret_cast<float4*>(sA + off) = hi;
-        *reinterpret_cast<float4*>(sAl + off) = lo;
-        const float4 yr = make_float4(y.y, -y.x, y.w, -y.z);  // (Yi, −Yr)
-        split4(yr, hi, lo);
-        off += 4;  // row m0+1 (m0 even → same 8-row group)
-        *reinterpret_cast<float4*>(sA + off) = hi;
-        *reinterpret_cast<float4*>(sAl + off) = lo;
-        split4(x, hi, lo);
-        const int offb = (row & 7) * 4 + q * 32 + (row >> 3) * 256;
-        *reinterpret_cast<float4*>(sBh + offb) = hi;
-        *reinterpret_cast<float4*>(sBl + offb) = lo;
       }
     } else {
-      // 32 columns; each is a contiguous row of 2χ floats → MN-major SW128_32B tiles for both operands
-      const int w4 = chi >> 1;  // float4 per row (2χ floats)
-      const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
-      for (int idx = tid; idx < SCOLS * w4; idx += TC_THREADS) {
-        const int kl = idx / w4, l = idx - kl * w4;
-        const unsigned col = k0 + kl;
-        float4 y = make_float4(0.f, 0.f, 0.f, 0.f), x = y;
-        if (col < ce) {
-          const long long a = (long long)col * chi + 2 * l;
-          y = __ldg(reinterpret_cast<const float4*>(t.Y + a));
-          x = __ldg(reinterpret_cast<const float4*>(t.X + a));
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
+        const unsigned col = k0 + it_row[j];
+        if (it_ok[j] && col < ce) {
+          const long long a = (long long)col * chi + 2 * it_q[j];
+          y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
         }
-        const int r = kl & 3, ak = kl >> 2, am = l >> 3, c = (l & 7) >> 1, half = l & 1;
-        const int inatom = r * 128 + ((c ^ r) * 32) + half * 16;
+      }
+    }
+  };
+#pragma unroll
+  for (int p = 0; p < PD; ++p)
+    if (p < nstage) load_stage(p, rx[p], ry[p]);
+
+  for (int st0 = 0; st0 < nstage; st0 += PD) {
+#pragma unroll
+    for (int p = 0; p < PD; ++p) {
+      const int st = st0 + p;
+      if (st >= nstage) break;
+      const int bsel = st & 1;
+      float* sA = smem + bsel * stage_floats;
+      float* sAl = sA + a_floats;
+      float* sBh = sAl + a_floats;
+      float* sBl = sBh + b_floats;
+      if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }  // MMAs that read this stage are done
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        if (!it_ok[j]) continue;
+        const float4 x = rx[p][j], y = ry[p][j];
         float4 hi, lo;
-        split4(x, hi, lo);  // A = X (conjugated side: rows (i,ri))
-        int off = (am * 512 + ak * sboA + inatom) >> 2;
-        *reinterpret_cast<float4*>(sA + off) = hi;
-        *reinterpret_cast<float4*>(sAl + off) = lo;
-        split4(y, hi, lo);
-        off = (am * 512 + ak * sboB + inatom) >> 2;
-        *reinterpret_cast<float4*>(sBh + off) = hi;
-        *reinterpret_cast<float4*>(sBl + off) = lo;
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;");
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint32_t a_base = smem_u32(term == 2 ? sAl : sA);
-        const uint32_t b_base = smem_u32(term == 1 ? sBl : sBh);
-#pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks) {
-          uint64_t ad, bd;
-          if (!LAST) {
-            ad = make_desc(a_base + ks * 256, 128, 1024, 0);
-            bd = make_desc(b_base + ks * 256, 128, 1024, 0);
-          } else {
-            const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
-            ad = make_desc(a_base + ks * 2 * sboA, 512, sboA, 1);
-            bd = make_desc(b_base + ks * 2 * sboB, 512, sboB, 1);
-          }
-          mma_tf32(tmem, ad, bd, idesc, (st | term | ks) != 0);
+        if (!LAST) {
+          split4(y, hi, lo);
+          *reinterpret_cast<float4*>(sA + offA[j]) = hi;
+          *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
+          const float4 yr = make_float4(y.y, -y.x, y.w, -y.z);  // (Yi, −Yr)
+          split4(yr, hi, lo);
+          *reinterpret_cast<float4*>(sA + offA[j] + 4) = hi;  // row m0+1 (m0 even → same 8-row group)
+          *reinterpret_cast<float4*>(sAl + offA[j] + 4) = lo;
+          split4(x, hi, lo);
+          *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
+          *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
+        } else {
+          split4(x, hi, lo);  // A = X (conjugated side: rows (i,ri))
+          *reinterpret_cast<float4*>(sA + offA[j]) = hi;
+          *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
+          split4(y, hi, lo);
+          *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
+          *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[bsel])) : "memory");
+      if (st + PD < nstage) load_stage(st + PD, rx[p], ry[p]);  // refill this ring slot
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a_base = smem_u32(term == 2 ? sAl : sA);
+          const uint32_t b_base = smem_u32(term == 1 ? sBl : sBh);
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            uint64_t ad, bd;
+            if (!LAST) {
+              ad = make_desc(a_base + ks * 256, 128, 1024, 0);
+              bd = make_desc(b_base + ks * 256, 128, 1024, 0);
+            } else {
+              ad = make_desc(a_base + ks * 2 * sboA, 512, sboA, 1);
+              bd = make_desc(b_base + ks * 2 * sboB, 512, sboB, 1);
+            }
+            mma_tf32(tmem, ad, bd, idesc, (st | term | ks) != 0);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[bsel])) : "memory");
+      }
+      used[bsel] = 1;
     }
-    used[bsel] = 1;
   }
   // drain: wait for the last commit of each stage buffer (commits complete in issue order)
   for (int bsel = 0; bsel < 2; ++bsel)

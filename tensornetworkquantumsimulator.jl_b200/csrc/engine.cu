@@ -81,6 +81,8 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
   { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_DMMA"); use_dmma_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_CLUSTER_JACOBI"); use_cluster_jacobi_ = !(e && e[0] == '0'); }
   cudaMemPool_t pool;
   TNQS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
   uint64_t thr = UINT64_MAX;
@@ -108,6 +110,8 @@ Engine::Engine(const Engine& o)
     : dtype_(o.dtype_), esz_(o.esz_), device_(o.device_), nv_(o.nv_), ne_(o.ne_), eu_(o.eu_), ev_(o.ev_),
       phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
   use_tc_ = o.use_tc_;
+  use_cluster_jacobi_ = o.use_cluster_jacobi_;
+  use_dmma_ = o.use_dmma_;
   profiling_ = o.profiling_;
   comm_ = o.comm_; owner_ = o.owner_; rank_ = o.rank_; nranks_ = o.nranks_;
   TNQS_CUDA(cudaSetDevice(device_));
@@ -706,6 +710,67 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       TNQS_CUDA(cudaGetLastError());
     }
   }
+  // ---- fp64 tensor-core path (kernels_dmma.cuh): Hermitian Gram of a tensor with itself, fp64 accumulation ----
+  if (acc_double && use_dmma_) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const bool inner1 = pass == 1;
+      std::vector<GramTask> grp;
+      std::vector<int> ids;
+      int maxMM = 0;
+      long long work = 0;
+      for (size_t i = 0; i < tasks.size(); ++i) {
+        const GramTask& t = tasks[i];
+        if (done[i] || (t.inner == 1) != inner1) continue;
+        if (t.X != t.Y || t.xps != t.yps || t.MM < 16 || t.MM > 128 || t.CC < 512) continue;
+        grp.push_back(t); ids.push_back((int)i); maxMM = std::max(maxMM, t.MM); work += t.CC;
+        done[i] = 1;
+      }
+      if (grp.empty()) continue;
+      static bool attr_set = false;
+      if (!attr_set) {
+        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_set = true;
+      }
+      // ~4 CTAs per SM overall, at least 1024 columns per split
+      const long long target_cols = std::max<long long>(1024, work / (148 * 4));
+      int maxsplit = 1, maxgroups = 1;
+      for (size_t k = 0; k < grp.size(); ++k) {
+        GramTask& t = grp[k];
+        long long ns = std::max<long long>(1, std::min<long long>(4096, (t.CC + target_cols - 1) / target_cols));
+        unsigned cps = (unsigned)((t.CC + ns - 1) / ns);
+        cps = (cps + DG_KCH - 1) / DG_KCH * DG_KCH;
+        t.cols_per_split = cps;
+        t.nsplit = (int)((t.CC + cps - 1) / cps);
+        t.partial = (double2*)talloc((size_t)t.nsplit * t.MM * t.MM * sizeof(double2));
+        maxsplit = std::max(maxsplit, t.nsplit);
+        const int R32 = (2 * t.MM + 31) / 32, nblk = R32 * (R32 + 1) / 2;
+        maxgroups = std::max(maxgroups, (nblk + DG_WARPS - 1) / DG_WARPS);
+        ReduceTask& r = red[ids[k]];
+        r.partial = t.partial; r.out = outs[ids[k]]; r.nsplit = t.nsplit; r.MM = t.MM; r.transpose = transpose ? 1 : 0;
+        stats_.gram_flops += 8.0 * t.MM * t.MM * (double)t.CC;
+      }
+      const int prow = (2 * maxMM + 31) / 32 * 32;
+      const size_t smem = (size_t)2 * prow * DG_LD * sizeof(double);
+      GramTask* d = upload(grp);
+      for (int off = 0; off < (int)grp.size(); off += 65535) {
+        const int nbz = std::min(65535, (int)grp.size() - off);
+        dim3 grid(maxsplit, maxgroups, nbz);
+        if (c64()) {
+          if (inner1) gram_dmma_kernel<float, true><<<grid, DG_THREADS, smem, stream_>>>(d + off);
+          else gram_dmma_kernel<float, false><<<grid, DG_THREADS, smem, stream_>>>(d + off);
+        } else {
+          if (inner1) gram_dmma_kernel<double, true><<<grid, DG_THREADS, smem, stream_>>>(d + off);
+          else gram_dmma_kernel<double, false><<<grid, DG_THREADS, smem, stream_>>>(d + off);
+        }
+        count_launch();
+        stats_.gram_launches += 1;
+      }
+      TNQS_CUDA(cudaGetLastError());
+    }
+  }
   for (int pass = 0; pass < 2; ++pass) {
     const bool inner1 = pass == 1;
     std::vector<GramTask> grp;
@@ -767,18 +832,88 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   TNQS_CUDA(cudaGetLastError());
 }
 
-void Engine::launch_jacobi(std::vector<JacobiTask>& tasks) {
+template <int LPP, int RPL>
+static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntasks, int BC, int C, int ld, size_t smem,
+                                  double dead_rel2, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ntasks * C));
+  cfg.blockDim = dim3((unsigned)std::max(32, BC * LPP));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2));
+}
+
+void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
   if (tasks.empty()) return;
   ProfScope ps(this, profiling_, stream_, ev0_, ev1_, &stats_.small_ms);
-  int maxn = 0;
-  for (auto& t : tasks) maxn = std::max(maxn, t.n);
-  const int pairs = (maxn + 1) / 2;
-  int maxm = 0;
-  for (auto& t : tasks) maxm = std::max(maxm, std::max(t.m, t.n));
-  const int maxwarps = maxm <= 128 ? 32 : (maxm <= 256 ? 16 : 8);  // register budget per lane grows with m
-  const int warps = std::max(1, std::min(maxwarps, pairs));
+  int maxn = 0, maxm = 0, maxmt = 0;
+  for (auto& t : tasks) {
+    maxn = std::max(maxn, t.n);
+    maxm = std::max(maxm, std::max(t.m, t.n));
+    maxmt = std::max(maxmt, t.m + (t.V ? t.n : 0));
+  }
   JacobiTask* d = upload(tasks);
   const unsigned nb = (unsigned)tasks.size();
+  if (maxmt <= 256 && maxn <= 256 && use_cluster_jacobi_) {
+    // shared-memory cluster kernel (kernels_jacobi.cuh)
+    const int LPP = maxmt <= 128 ? 16 : 32;
+    int RPL = 1;
+    while (RPL * LPP < maxmt) RPL <<= 1;
+    int npad = 2;
+    while (npad < maxn) npad <<= 1;
+    const int ld = maxmt;
+    int BC, C;
+    if (npad <= 32) { BC = npad / 2; C = 1; }
+    else {
+      // both splits run n−1 rounds per sweep; take the one that needs fewer waves of CTAs, then the larger block
+      auto waves = [&](int bc) {
+        const int c = npad / (2 * bc);
+        const size_t sm = (size_t)2 * bc * ld * sizeof(double2) + 2048;
+        const int thr = bc * LPP;
+        const int per_sm = std::max(1, (int)std::min<size_t>(std::min<size_t>(227 * 1024 / sm, 2048 / thr), 65536 / (thr * (RPL >= 8 ? 128 : 64))));
+        return (int)(((long long)nb * c + 148ll * per_sm - 1) / (148ll * per_sm));
+      };
+      const bool can16 = npad / 32 <= 8, can8 = npad / 16 <= 8;
+      if (can16 && (!can8 || waves(16) <= waves(8))) { BC = 16; C = npad / 32; }
+      else { BC = 8; C = npad / 16; }
+    }
+    const size_t smem = (size_t)2 * BC * ld * sizeof(double2);
+    JacobiAux* aux = (JacobiAux*)talloc(sizeof(JacobiAux) * nb);
+    TNQS_CUDA(cudaMemsetAsync(aux, 0, sizeof(JacobiAux) * nb, stream_));
+    if (LPP == 16) {
+      if (RPL <= 1) launch_jacobi_cluster<16, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+      else if (RPL == 2) launch_jacobi_cluster<16, 2>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+      else if (RPL == 4) launch_jacobi_cluster<16, 4>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+      else launch_jacobi_cluster<16, 8>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+    } else {
+      launch_jacobi_cluster<32, 8>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+    }
+    count_launch();
+    TNQS_CUDA(cudaGetLastError());
+    const bool dbg = std::getenv("TNQS_JACOBI_DEBUG") != nullptr;
+    if (dbg) {  // sweeps actually run per matrix (rot[s] is set by every sweep that rotated something)
+      std::vector<JacobiAux> h(nb);
+      TNQS_CUDA(cudaMemcpyAsync(h.data(), aux, sizeof(JacobiAux) * nb, cudaMemcpyDeviceToHost, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));
+      int mn = 1000, mx = 0; double avg = 0;
+      for (auto& a : h) { int c = 0; for (int i = 0; i < 64; ++i) c += a.rot[i] != 0; mn = std::min(mn, c); mx = std::max(mx, c); avg += c; }
+      std::fprintf(stderr, "[jacobi] tasks=%u maxn=%d maxmt=%d LPP=%d RPL=%d BC=%d C=%d smem=%zu rotating sweeps min/avg/max=%d/%.1f/%d\n",
+                   nb, maxn, maxmt, LPP, RPL, BC, C, smem, mn, avg / nb, mx);
+    }
+    return;
+  }
+  const int pairs = (maxn + 1) / 2;
+  const int maxwarps = maxm <= 128 ? 32 : (maxm <= 256 ? 16 : 8);  // register budget per lane grows with m
+  const int warps = std::max(1, std::min(maxwarps, pairs));
   if (maxm <= 32) jacobi_kernel<1><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
   else if (maxm <= 64) jacobi_kernel<2><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
   else if (maxm <= 128) jacobi_kernel<4><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
@@ -1181,7 +1316,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         jt[i].sval = (double*)talloc(sizeof(double) * mt[i].chi);
         jt[i].perm = (int*)talloc(sizeof(int) * mt[i].chi);
       }
-      launch_jacobi(jt);
+      launch_jacobi(jt, 1e-40);  // message eigenvalues are kept down to the absolute sqrt_cutoff: no early null columns
       if (c64()) msg_finish_kernel<float><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm, sqrt_cutoff);
       else msg_finish_kernel<double><<<(unsigned)mt.size(), 256, 0, stream_>>>(dm, sqrt_cutoff);
       count_launch();
@@ -1250,7 +1385,8 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       HermTask* dh = upload(ht);
       herm_prepare_kernel<<<2 * ng, 256, 0, stream_>>>(dh);
       count_launch();
-      launch_jacobi(jg);
+      // directions with λ ≤ 64·eps·λmax are dropped by su_theta: columns below 1e-15·‖G‖_F may stop rotating early
+      launch_jacobi(jg, 1e-30);
       std::vector<JacobiTask> jt(ng);
       for (int k = 0; k < ng; ++k) {
         const int g = gate_ids[gpos + k];
@@ -1294,7 +1430,8 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       SuGateTask* ds = upload(st);
       su_theta_kernel<<<ng, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
       count_launch();
-      launch_jacobi(jt);
+      // singular values below 1e-13·‖θ‖_F never survive the truncation (σ² < 1e-26 of the total weight)
+      launch_jacobi(jt, 1e-26);
       su_truncate_kernel<<<(ng + 63) / 64, 64, 0, stream_>>>(ds, ng, ao.maxdim, ao.mindim, ao.cutoff);
       count_launch();
       TNQS_CUDA(cudaGetLastError());

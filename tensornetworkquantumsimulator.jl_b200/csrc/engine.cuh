@@ -20,6 +20,7 @@
 #include "kernels_small.cuh"
 #include "kernels_tensor.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_dmma.cuh"
 
 namespace tnqs {
 
@@ -120,6 +121,8 @@ class Engine {
   bool profiling_ = false;
   int wall_depth_ = 0;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
+  bool use_dmma_ = true;            // fp64 tensor-core Hermitian Gram (env TNQS_DMMA=0: SIMT fp64 kernel)
+  bool use_cluster_jacobi_ = true;  // shared-memory cluster Jacobi (env TNQS_CLUSTER_JACOBI=0: L2-resident kernel)
   std::shared_ptr<CommHandle> comm_;  // null: single GPU
   std::vector<int> owner_;            // owner rank per vertex (empty: everything local)
   int rank_ = 0, nranks_ = 1;
@@ -147,7 +150,7 @@ class Engine {
   std::vector<ModeTask> launch_mode_tc(std::vector<ModeTask>& tasks);
   void launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vector<double2*>& outs,
                    bool transpose);
-  void launch_jacobi(std::vector<JacobiTask>& tasks);
+  void launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2);
   void run_chains(std::vector<Chain>& chains);
   ModeTask mode_task(int v, int pos, const void* in, void* out, const void* mat) const;
   GramTask gram_task(int v, int pos, int planes, const void* X, const void* Y) const;

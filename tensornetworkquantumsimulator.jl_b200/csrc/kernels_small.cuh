@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "kernels_tensor.cuh"
+#include "kernels_jacobi.cuh"
 
 namespace tnqs {
 
@@ -39,16 +40,9 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one-sided Jacobi
+// one-sided Jacobi, global-memory (L2) resident: the fallback for matrices too large for the
+// shared-memory cluster kernel of kernels_jacobi.cuh (stacked rows > 256 or more than 256 columns)
 // ------------------------------------------------------------------------------------------------
-struct JacobiTask {
-  double2* A;    // m×n column-major, overwritten by A·V (columns = σ_j u_j)
-  double2* V;    // n×n column-major accumulated right rotations, or nullptr
-  int m, n;
-  double* sval;  // [n] column norms of the result
-  int* perm;     // [n] column indices by descending sval
-};
-
 // RPL = rows held per lane: each lane keeps its rows of both columns of a pair in registers, so a
 // pair costs one L2 round trip (all loads issued back to back) instead of one per row chunk.
 template <int RPL>
@@ -429,12 +423,23 @@ __global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
   const int n0 = d0 * chi, n1 = d1 * chi;
   const int rows = n0 * d0, cols = n1 * d1;
   const int keep = *t.keep;
+  // Numerically null directions (σ_c ≤ 2e-13·‖θ‖_F: the Jacobi stops rotating such columns, so they are
+  // not orthogonal to the others in the relative sense) get zero factor columns instead of noise/σ^{3/2};
+  // their weight σ_c·u_c v_c† in the two-site tensor is below 2e-13 either way.
+  __shared__ double s_thr;
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int k = 0; k < cols; ++k) tot += t.sigma[k] * t.sigma[k];
+    s_thr = 2e-13 * sqrt(tot);
+  }
+  __syncthreads();
+  const double sthr = s_thr;
   // right factor: Rp[κ, c] = Σ_ρ θ0[ρ,κ] conj(Uσ[ρ, perm c]) / σ_c^{3/2}
   for (int idx = threadIdx.x; idx < cols * keep; idx += blockDim.x) {
     const int kap = idx % cols, c = idx / cols;
     const double sg = t.sigma[c];
     double2 acc; acc.x = 0; acc.y = 0;
-    if (sg > 0) {
+    if (sg > sthr) {
       const double2* th = t.theta0 + (long long)kap * rows;
       const double2* u = t.theta + (long long)t.perm[c] * rows;
       for (int rho = 0; rho < rows; ++rho) {
@@ -457,7 +462,7 @@ __global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
       const int sp = col / keep, c = col - sp * keep;
       const double sg = t.sigma[c];
       double2 acc; acc.x = 0; acc.y = 0;
-      if (sg > 0) {
+      if (sg > sthr) {
         const double2* u = t.theta + (long long)t.perm[c] * rows;
         for (int r = 0; r < n0; ++r) {
           const double w = t.isq[0][r];

@@ -23,6 +23,7 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*Broadcast)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
@@ -48,6 +49,7 @@ struct NcclApi {
       api.CommDestroy = (int (*)(NcclComm))sym("ncclCommDestroy");
       api.Broadcast = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclBroadcast");
       api.AllReduce = (int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t))sym("ncclAllReduce");
+      api.AllGather = (int (*)(const void*, void*, size_t, int, NcclComm, cudaStream_t))sym("ncclAllGather");
       api.GroupStart = (int (*)())sym("ncclGroupStart");
       api.GroupEnd = (int (*)())sym("ncclGroupEnd");
       api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");

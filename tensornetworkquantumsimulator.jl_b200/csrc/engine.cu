@@ -832,12 +832,12 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   TNQS_CUDA(cudaGetLastError());
 }
 
-template <int LPP, int RPL>
+template <int LPP, int RPL, int MAXT, int MINB>
 static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntasks, int BC, int C, int ld, size_t smem,
                                   double dead_rel2, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
-    TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
@@ -849,7 +849,7 @@ static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntask
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
-  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2));
+  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2));
 }
 
 void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
@@ -865,12 +865,13 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
   const unsigned nb = (unsigned)tasks.size();
   if (maxmt <= 256 && maxn <= 256 && use_cluster_jacobi_) {
     // shared-memory cluster kernel (kernels_jacobi.cuh)
-    const int LPP = maxmt <= 128 ? 16 : 32;
+    int LPP = maxmt <= 128 ? 16 : 32;
+    if (const char* e = std::getenv("TNQS_JACOBI_LPP")) { if (std::atoi(e) == 32 && maxmt > 32) LPP = 32; }  // tuning override
     int RPL = 1;
     while (RPL * LPP < maxmt) RPL <<= 1;
     int npad = 2;
     while (npad < maxn) npad <<= 1;
-    const int ld = maxmt;
+    const int ld = RPL * LPP;  // ≥ maxmt: the pad rows of every shared-memory column are kept at zero
     int BC, C;
     if (npad <= 32) { BC = npad / 2; C = 1; }
     else {
@@ -885,18 +886,31 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
       const bool can16 = npad / 32 <= 8, can8 = npad / 16 <= 8;
       if (can16 && (!can8 || waves(16) <= waves(8))) { BC = 16; C = npad / 32; }
       else { BC = 8; C = npad / 16; }
+      if (const char* e = std::getenv("TNQS_JACOBI_BC")) {  // tuning override
+        const int want = std::atoi(e);
+        if (want == 8 && can8) { BC = 8; C = npad / 16; }
+        if (want == 16 && can16) { BC = 16; C = npad / 32; }
+      }
     }
     const size_t smem = (size_t)2 * BC * ld * sizeof(double2);
     JacobiAux* aux = (JacobiAux*)talloc(sizeof(JacobiAux) * nb);
     TNQS_CUDA(cudaMemsetAsync(aux, 0, sizeof(JacobiAux) * nb, stream_));
+    // register budget: MINB CTAs of MAXT threads per SM
+    const int thr = std::max(32, BC * LPP);
+#define TNQS_JAC(L, R) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
+    else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
+    else launch_jacobi_cluster<L, R, 512, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); } while (0)
     if (LPP == 16) {
-      if (RPL <= 1) launch_jacobi_cluster<16, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
-      else if (RPL == 2) launch_jacobi_cluster<16, 2>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
-      else if (RPL == 4) launch_jacobi_cluster<16, 4>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
-      else launch_jacobi_cluster<16, 8>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+      if (RPL <= 1) TNQS_JAC(16, 1);
+      else if (RPL == 2) TNQS_JAC(16, 2);
+      else if (RPL == 4) TNQS_JAC(16, 4);
+      else TNQS_JAC(16, 8);
     } else {
-      launch_jacobi_cluster<32, 8>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_);
+      if (RPL <= 2) TNQS_JAC(32, 2);
+      else if (RPL == 4) TNQS_JAC(32, 4);
+      else TNQS_JAC(32, 8);
     }
+#undef TNQS_JAC
     count_launch();
     TNQS_CUDA(cudaGetLastError());
     const bool dbg = std::getenv("TNQS_JACOBI_DEBUG") != nullptr;
@@ -1365,38 +1379,86 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
     }
 
     // ---- 4. eig(G), θ, SVD(θ), truncation ------------------------------------------------------
+    // Multi-GPU: the O(χ³) factorisations of gate k run on rank k mod R only (its "solver"); the kept
+    // rank, truncation error, singular values and the two new factors then reach every rank with two
+    // all-gathers over packed, rank-major records.
+    const int R = nranks_ > 1 ? nranks_ : 1;
+    const int per = (ng + R - 1) / R;
+    auto solver = [&](int k) { return R > 1 ? k % R : rank_; };
+    auto slot = [&](int k) { return R > 1 ? (k % R) * per + k / R : k; };
     std::vector<SuGateTask> st(ng);
-    int* d_keep = (int*)talloc(sizeof(int) * ng);
-    double* d_err = (double*)talloc(sizeof(double) * ng);
-    double* d_ss = (double*)talloc(sizeof(double) * ng);
     std::vector<int> keep_cap(ng);
-    {
-      std::vector<HermTask> ht(2 * ng);
-      std::vector<JacobiTask> jg(2 * ng);
-      for (int i = 0; i < 2 * ng; ++i) {
-        const int n = nn[i];
-        ht[i].G = G[i]; ht[i].n = n;
-        ht[i].A = (double2*)talloc((size_t)n * n * sizeof(double2));
-        ht[i].V = (double2*)talloc((size_t)n * n * sizeof(double2));
-        jg[i].A = ht[i].A; jg[i].V = ht[i].V; jg[i].m = jg[i].n = n;
-        jg[i].sval = (double*)talloc(sizeof(double) * n);
-        jg[i].perm = (int*)talloc(sizeof(int) * n);
+    int maxcols = 1;
+    size_t xstride = 256;
+    for (int k = 0; k < ng; ++k) {
+      const int g = gate_ids[gpos + k];
+      const int d0 = phys_[verts[2 * g]], d1 = phys_[verts[2 * g + 1]];
+      const int chi = bond_[ebond[k]];
+      // thin QR of the reference: r_s = min(∏ external dims, d_s·χ_b)  (simple_update.jl:47-48)
+      long long full = 1ll << 40;
+      for (int s = 0; s < 2; ++s) {
+        const int v = verts[2 * g + s];
+        const long long ext = site_elems(v) / ((long long)phys_[v] * chi);
+        full = std::min(full, std::min<long long>(ext, nn[2 * k + s]) * phys_[v]);
       }
-      HermTask* dh = upload(ht);
-      herm_prepare_kernel<<<2 * ng, 256, 0, stream_>>>(dh);
-      count_launch();
-      // directions with λ ≤ 64·eps·λmax are dropped by su_theta: columns below 1e-15·‖G‖_F may stop rotating early
-      launch_jacobi(jg, 1e-30);
-      std::vector<JacobiTask> jt(ng);
-      for (int k = 0; k < ng; ++k) {
+      int cap = (int)full;
+      if (ao.maxdim > 0) cap = std::min(cap, std::max(ao.maxdim, std::max(1, ao.mindim)));
+      keep_cap[k] = cap;
+      SuGateTask& t = st[k];
+      std::memset(&t, 0, sizeof(t));
+      t.full = (int)full;
+      maxcols = std::max(maxcols, nn[2 * k + 1] * d1);
+      const size_t x0 = ((size_t)nn[2 * k] * d0 * cap * esz_ + 255) & ~size_t(255);
+      const size_t x1 = ((size_t)nn[2 * k + 1] * d1 * cap * esz_ + 255) & ~size_t(255);
+      xstride = std::max(xstride, x0 + x1);
+    }
+    const size_t rec_bytes = 32 + sizeof(double) * (size_t)maxcols;  // {err, Σkept σ², keep, pad, σ[maxcols]}
+    char* d_rec = (char*)talloc(rec_bytes * (size_t)R * per);
+    char* d_x = (char*)talloc(xstride * (size_t)R * per);
+    std::vector<int> mine;
+    for (int k = 0; k < ng; ++k) {
+      const int g = gate_ids[gpos + k];
+      SuGateTask& t = st[k];
+      const int d0 = phys_[verts[2 * g]], d1 = phys_[verts[2 * g + 1]];
+      char* rec = d_rec + rec_bytes * (size_t)slot(k);
+      t.err = (double*)rec; t.sumsq_kept = (double*)(rec + 8); t.keep = (int*)(rec + 16); t.sigma = (double*)(rec + 32);
+      char* xb = d_x + xstride * (size_t)slot(k);
+      t.X[0] = xb;
+      t.X[1] = xb + (((size_t)nn[2 * k] * d0 * keep_cap[k] * esz_ + 255) & ~size_t(255));
+      t.d[0] = d0; t.d[1] = d1; t.chi_b = bond_[ebond[k]];
+      if (solver(k) == rank_) mine.push_back(k);
+    }
+    {
+      const int nm = (int)mine.size();
+      std::vector<HermTask> ht(2 * nm);
+      std::vector<JacobiTask> jg(2 * nm);
+      for (int q = 0; q < nm; ++q)
+        for (int s = 0; s < 2; ++s) {
+          const int i = 2 * mine[q] + s, j = 2 * q + s;
+          const int n = nn[i];
+          ht[j].G = G[i]; ht[j].n = n;
+          ht[j].A = (double2*)talloc((size_t)n * n * sizeof(double2));
+          ht[j].V = (double2*)talloc((size_t)n * n * sizeof(double2));
+          jg[j].A = ht[j].A; jg[j].V = ht[j].V; jg[j].m = jg[j].n = n;
+          jg[j].sval = (double*)talloc(sizeof(double) * n);
+          jg[j].perm = (int*)talloc(sizeof(int) * n);
+        }
+      if (nm > 0) {
+        HermTask* dh = upload(ht);
+        herm_prepare_kernel<<<2 * nm, 256, 0, stream_>>>(dh);
+        count_launch();
+        // directions with λ ≤ 64·eps·λmax are dropped by su_theta: columns below 1e-15·‖G‖_F may stop rotating early
+        launch_jacobi(jg, 1e-30);
+      }
+      std::vector<JacobiTask> jt(nm);
+      std::vector<SuGateTask> stm(nm);
+      for (int q = 0; q < nm; ++q) {
+        const int k = mine[q];
         const int g = gate_ids[gpos + k];
         SuGateTask& t = st[k];
-        std::memset(&t, 0, sizeof(t));
-        const int d0 = phys_[verts[2 * g]], d1 = phys_[verts[2 * g + 1]];
-        const int chi = bond_[ebond[k]];
-        t.d[0] = d0; t.d[1] = d1; t.chi_b = chi;
+        const int d0 = t.d[0], d1 = t.d[1];
         for (int s = 0; s < 2; ++s) {
-          t.GA[s] = ht[2 * k + s].A; t.GV[s] = ht[2 * k + s].V;
+          t.GA[s] = ht[2 * q + s].A; t.GV[s] = ht[2 * q + s].V;
           t.sq[s] = (double*)talloc(sizeof(double) * nn[2 * k + s]);
           t.isq[s] = (double*)talloc(sizeof(double) * nn[2 * k + s]);
         }
@@ -1409,50 +1471,62 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         double* sval = (double*)talloc(sizeof(double) * cols);
         int* perm = (int*)talloc(sizeof(int) * cols);
         t.sval = sval; t.perm = perm;
-        t.sigma = (double*)talloc(sizeof(double) * cols);
-        t.keep = d_keep + k; t.err = d_err + k; t.sumsq_kept = d_ss + k;
-        // thin QR of the reference: r_s = min(∏ external dims, d_s·χ_b)  (simple_update.jl:47-48)
-        long long full = 1ll << 40;
-        for (int s = 0; s < 2; ++s) {
-          const int v = verts[2 * g + s];
-          const long long ext = site_elems(v) / ((long long)phys_[v] * chi);
-          full = std::min(full, std::min<long long>(ext, nn[2 * k + s]) * phys_[v]);
-        }
-        t.full = (int)full;
-        int cap = (int)full;
-        if (ao.maxdim > 0) cap = std::min(cap, std::max(ao.maxdim, std::max(1, ao.mindim)));
-        keep_cap[k] = cap;
-        t.Rp = (double2*)talloc((size_t)cols * cap * sizeof(double2));
-        t.X[0] = talloc((size_t)nn[2 * k] * d0 * cap * esz_);
-        t.X[1] = talloc((size_t)nn[2 * k + 1] * d1 * cap * esz_);
-        jt[k].A = t.theta; jt[k].V = nullptr; jt[k].m = rows; jt[k].n = cols; jt[k].sval = sval; jt[k].perm = perm;
+        t.Rp = (double2*)talloc((size_t)cols * keep_cap[k] * sizeof(double2));
+        jt[q].A = t.theta; jt[q].V = nullptr; jt[q].m = rows; jt[q].n = cols; jt[q].sval = sval; jt[q].perm = perm;
+        stm[q] = t;
       }
-      SuGateTask* ds = upload(st);
-      su_theta_kernel<<<ng, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
-      count_launch();
-      // singular values below 1e-13·‖θ‖_F never survive the truncation (σ² < 1e-26 of the total weight)
-      launch_jacobi(jt, 1e-26);
-      su_truncate_kernel<<<(ng + 63) / 64, 64, 0, stream_>>>(ds, ng, ao.maxdim, ao.mindim, ao.cutoff);
-      count_launch();
-      TNQS_CUDA(cudaGetLastError());
+      SuGateTask* ds = nullptr;
+      if (nm > 0) {
+        ds = upload(stm);
+        su_theta_kernel<<<nm, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
+        count_launch();
+        // singular values below 1e-13·‖θ‖_F never survive the truncation (σ² < 1e-26 of the total weight)
+        launch_jacobi(jt, 1e-26);
+        su_truncate_kernel<<<(nm + 63) / 64, 64, 0, stream_>>>(ds, nm, ao.maxdim, ao.mindim, ao.cutoff);
+        count_launch();
+        TNQS_CUDA(cudaGetLastError());
+      }
+      if (R > 1) {
+        NcclApi& api = NcclApi::get();
+        api.check(api.AllGather(d_rec + rec_bytes * (size_t)per * rank_, d_rec, rec_bytes * (size_t)per, kNcclChar, comm_->comm, stream_),
+                  "ncclAllGather(records)");
+        stats_.kernel_launches += 1;
+      }
       // the host needs the kept ranks to size the new tensors: the one sync of the batch
       std::vector<int> keep(ng), flags(2 * std::max<size_t>(1, mt.size()));
       std::vector<double> err(ng);
-      TNQS_CUDA(cudaMemcpyAsync(keep.data(), d_keep, sizeof(int) * ng, cudaMemcpyDeviceToHost, stream_));
-      TNQS_CUDA(cudaMemcpyAsync(err.data(), d_err, sizeof(double) * ng, cudaMemcpyDeviceToHost, stream_));
+      std::vector<char> h_rec(rec_bytes * (size_t)R * per);
+      TNQS_CUDA(cudaMemcpyAsync(h_rec.data(), d_rec, h_rec.size(), cudaMemcpyDeviceToHost, stream_));
       if (!mt.empty())
         TNQS_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * 2 * mt.size(), cudaMemcpyDeviceToHost, stream_));
       TNQS_CUDA(cudaStreamSynchronize(stream_));
+      for (int k = 0; k < ng; ++k) {
+        const char* rec = h_rec.data() + rec_bytes * (size_t)slot(k);
+        std::memcpy(&err[k], rec, sizeof(double));
+        std::memcpy(&keep[k], rec + 16, sizeof(int));
+        if (keep[k] < 1 || keep[k] > keep_cap[k]) {
+          free_temps();
+          throw Error(TNQS_ECUDA, "simple update: invalid kept rank returned by the truncation kernel");
+        }
+      }
       for (size_t i = 0; i < mt.size(); ++i)
         if (flags[2 * i + 1]) {
           free_temps();
           throw Error(TNQS_EDOMAIN, "DomainError: sqrt of a negative message eigenvalue (message into vertex " +
                                         std::to_string(verts[2 * gate_ids[gpos + envs[i].gate] + envs[i].site]) + ")");
         }
-      if (c64()) su_factors_kernel<float><<<ng, 256, 0, stream_>>>(ds);
-      else su_factors_kernel<double><<<ng, 256, 0, stream_>>>(ds);
-      count_launch();
-      TNQS_CUDA(cudaGetLastError());
+      if (nm > 0) {
+        if (c64()) su_factors_kernel<float><<<nm, 256, 0, stream_>>>(ds);
+        else su_factors_kernel<double><<<nm, 256, 0, stream_>>>(ds);
+        count_launch();
+        TNQS_CUDA(cudaGetLastError());
+      }
+      if (R > 1) {
+        NcclApi& api = NcclApi::get();
+        api.check(api.AllGather(d_x + xstride * (size_t)per * rank_, d_x, xstride * (size_t)per, kNcclChar, comm_->comm, stream_),
+                  "ncclAllGather(factors)");
+        stats_.kernel_launches += 1;
+      }
 
       // ---- 5. un-gauge with the projector and contract with the new factor (:62-64) -----------
       std::vector<Chain> proj(2 * ng);
@@ -1510,7 +1584,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           msg_set_[de] = 1;
           DiagTask d{};
           d.out = msg_[de]; d.chi = keep[k]; d.diag = st[k].sigma;
-          d.scale_sumsq = normalize ? d_ss + k : nullptr;
+          d.scale_sumsq = normalize ? st[k].sumsq_kept : nullptr;
           dt.push_back(d);
         }
         errs[g] = err[k];

@@ -48,16 +48,20 @@ __device__ __forceinline__ void rr_pair(int ne, int step, int pair, int& p, int&
   else { p = (step + pair) % (ne - 1); q = (step - pair + (ne - 1)) % (ne - 1); }
 }
 
-template <int LPP, int RPL>
-__global__ void __launch_bounds__(512) jacobi_cluster_kernel(const JacobiTask* __restrict__ tasks, JacobiAux* __restrict__ aux,
+template <int LPP, int RPL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const JacobiTask* __restrict__ tasks, JacobiAux* __restrict__ aux,
                                                              int BC, int C, int ld, int max_sweeps, double tol,
                                                              double dead_rel2) {
   extern __shared__ __align__(16) unsigned char jsm_raw[];
   double2* cols = reinterpret_cast<double2*>(jsm_raw);  // [2·BC][ld]
   __shared__ unsigned char s_dead[64];
   __shared__ int s_gcol[64];
-  __shared__ int s_rot;
+  __shared__ int s_rot, s_anyrot;
   __shared__ double s_red[16];
+  __shared__ double s_dot[16][4];    // per pair of the round: a, b, Re g, Im g
+  __shared__ double s_rotp[16][4];   // c, s, e^{-iφ}
+  __shared__ int s_pair[16][2], s_do[16];
+  __shared__ unsigned char s_sched[31][16][2];  // pair schedule of the first block-round (all pairs among 2·BC slots)
 
   const int task = blockIdx.x / C, crank = blockIdx.x - task * C;
   const JacobiTask t = tasks[task];
@@ -69,6 +73,18 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(const JacobiTask* _
   const int pi = tid / LPP, l = tid % LPP;          // pair slot of this lane group, lane inside it
   const unsigned gmask = (LPP == 32) ? 0xffffffffu : (0xffffu << (16 * ((tid & 31) >> 4)));
 
+  // rows ≥ mt of every shared-memory column stay zero (ld = LPP·RPL ≥ mt), so the row loops need no bound
+  // checks; the dot products run over the A part only: per-lane bit k set ⇔ row l + LPP·k < m
+  unsigned dotmask = 0;
+#pragma unroll
+  for (int k = 0; k < RPL; ++k) dotmask |= (unsigned)(l + LPP * k < m) << k;
+  for (int idx = tid; idx < (nslots - 1) * BC; idx += nthreads) {
+    const int r = idx / BC, p = idx - r * BC;
+    int a, b;
+    rr_pair(nslots, r, p, a, b);
+    if (a > b) { const int x = a; a = b; b = x; }
+    s_sched[r][p][0] = (unsigned char)a; s_sched[r][p][1] = (unsigned char)b;
+  }
   auto col_ptr = [&](int gcol, int row) -> double2* {  // global address of stacked row `row` of column gcol
     return row < m ? t.A + (long long)gcol * m + row : t.V + (long long)gcol * n + (row - m);
   };
@@ -78,20 +94,32 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(const JacobiTask* _
       s_gcol[s] = g < n ? g : -1;
       s_dead[s] = g < n ? __ldcg(&ax->dead[g]) : 1;
     }
-    for (int idx = tid; idx < nslots * mt; idx += nthreads) {
-      const int s = idx / mt, row = idx - s * mt;
-      const int g = (s < BC ? bp : bq) * BC + (s % BC);
-      double2 v; v.x = 0; v.y = 0;
-      if (g < n) v = __ldcg(col_ptr(g, row));
-      cols[s * ld + row] = v;
+    // ld is a power of two; 8 independent L2 loads in flight per thread before the first store
+    const int total = nslots * ld, ldsh = 31 - __clz(ld);
+    for (int base = tid; base < total; base += 8 * nthreads) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * nthreads;
+        const int s = idx >> ldsh, row = idx & (ld - 1);
+        const int g = (s < BC ? bp : bq) * BC + (s & (BC - 1));
+        v[u].x = 0; v[u].y = 0;
+        if (idx < total && g < n && row < mt) v[u] = __ldcg(col_ptr(g, row));
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * nthreads;
+        if (idx < total) cols[idx] = v[u];
+      }
     }
     __syncthreads();
   };
   auto store_blocks = [&]() {
-    for (int idx = tid; idx < nslots * mt; idx += nthreads) {
-      const int s = idx / mt, row = idx - s * mt;
+    const int total = nslots * ld, ldsh = 31 - __clz(ld);
+    for (int idx = tid; idx < total; idx += nthreads) {
+      const int s = idx >> ldsh, row = idx & (ld - 1);
       const int g = s_gcol[s];
-      if (g >= 0) __stcg(col_ptr(g, row), cols[s * ld + row]);
+      if (g >= 0 && row < mt) __stcg(col_ptr(g, row), cols[idx]);
     }
     for (int s = tid; s < nslots; s += nthreads)
       if (s_gcol[s] >= 0) ax->dead[s_gcol[s]] = s_dead[s];
@@ -140,22 +168,30 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(const JacobiTask* _
           __syncthreads();
         }
         const int nrounds = (bt == 0) ? nslots - 1 : BC;
+        double2 xr[RPL], yr[RPL];
         for (int r = 0; r < nrounds; ++r) {
+          // ---- phase A: every lane group loads its rows of the two columns and forms a, b, g ------------
           int s1 = 0, s2 = 1;
           if (pi >= BC) {}  // spare lanes of a block smaller than one warp only keep the barriers company
-          else if (bt == 0) { rr_pair(nslots, r, pi, s1, s2); if (s1 > s2) { const int x = s1; s1 = s2; s2 = x; } }
-          else { s1 = pi; s2 = BC + (pi + r) % BC; }
-          if (pi < BC && !(s_dead[s1] | s_dead[s2])) {
-            double2* __restrict__ cp = cols + s1 * ld;
-            double2* __restrict__ cq = cols + s2 * ld;
-            double2 xr[RPL], yr[RPL];
+          else if (bt == 0) { s1 = s_sched[r][pi][0]; s2 = s_sched[r][pi][1]; }
+          else { s1 = pi; s2 = pi + r; s2 = BC + (s2 >= BC ? s2 - BC : s2); }
+          const bool live = pi < BC && !(s_dead[s1] | s_dead[s2]);
+          double2* __restrict__ cp = cols + s1 * ld;
+          double2* __restrict__ cq = cols + s2 * ld;
+          // cross block-rounds: lane group pi keeps ITS column (slot pi) in registers for the whole visit and
+          // only the rotating partner goes through shared memory (halves the shared-memory traffic)
+          const bool xres = bt != 0;
+          if (xres && r == 0 && pi < BC) {
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) xr[k] = cp[l + LPP * k];
+          }
+          if (live) {
             double a = 0, b = 0, gx = 0, gy = 0;
 #pragma unroll
             for (int k = 0; k < RPL; ++k) {
-              const int i = l + LPP * k;
-              if (i < mt) { xr[k] = cp[i]; yr[k] = cq[i]; }
-              else { xr[k].x = xr[k].y = 0; yr[k].x = yr[k].y = 0; }
-              if (i < m) {
+              if (!xres) xr[k] = cp[l + LPP * k];
+              yr[k] = cq[l + LPP * k];
+              if ((dotmask >> k) & 1u) {
                 const double2 x = xr[k], y = yr[k];
                 a += x.x * x.x + x.y * x.y;
                 b += y.x * y.x + y.y * y.y;
@@ -170,37 +206,64 @@ __global__ void __launch_bounds__(512) jacobi_cluster_kernel(const JacobiTask* _
               gx += __shfl_xor_sync(gmask, gx, o);
               gy += __shfl_xor_sync(gmask, gy, o);
             }
-            const double g2 = gx * gx + gy * gy;
-            const bool alive_p = a > floor2, alive_q = b > floor2;
-            if (l == 0) {
-              if (!alive_p) s_dead[s1] = 1;
-              if (!alive_q) s_dead[s2] = 1;
-            }
-            if (alive_p && alive_q && g2 > tol2 * a * b) {
-              if (l == 0) s_rot = 1;
-              const double ig = rsqrt(g2);
-              const double zeta = 0.5 * (b - a) * ig;
-              const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-              const double c = rsqrt(1.0 + tt * tt), s = c * tt;
-              const double phx = gx * ig, phy = -gy * ig;  // e^{-iφ}
-#pragma unroll
-              for (int k = 0; k < RPL; ++k) {
-                const int i = l + LPP * k;
-                if (i < mt) {
-                  const double2 x = xr[k];
-                  double2 y;
-                  y.x = yr[k].x * phx - yr[k].y * phy;
-                  y.y = yr[k].x * phy + yr[k].y * phx;
-                  double2 xn, yn;
-                  xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
-                  yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
-                  cp[i] = xn; cq[i] = yn;
-                }
+            if (l == 0) { s_dot[pi][0] = a; s_dot[pi][1] = b; s_dot[pi][2] = gx; s_dot[pi][3] = gy; s_pair[pi][0] = s1; s_pair[pi][1] = s2; }
+          } else if (l == 0 && pi < BC) {
+            s_pair[pi][0] = -1;
+          }
+          if (!__syncthreads_or(live ? 1 : 0)) continue;  // nothing alive in this round
+          // ---- phase B: one warp turns the BC dot products into rotations (the fp64 rsqrt chains are
+          //      issued once per round instead of once per lane group) ---------------------------------------
+          if (tid < 32) {
+            bool rotate = false;
+            if (tid < BC && s_pair[tid][0] >= 0) {
+              const double a = s_dot[tid][0], b = s_dot[tid][1], gx = s_dot[tid][2], gy = s_dot[tid][3];
+              const double g2 = gx * gx + gy * gy;
+              const bool alive_p = a > floor2, alive_q = b > floor2;
+              if (!alive_p) s_dead[s_pair[tid][0]] = 1;
+              if (!alive_q) s_dead[s_pair[tid][1]] = 1;
+              if (alive_p && alive_q && g2 > tol2 * a * b) {
+                rotate = true;
+                // ζ = δ/2|g|, t = sgn(δ)/(|ζ|+√(1+ζ²))  ⇒  c² = ½ + ½|δ|/h,  s = sgn(δ)·|g|/(h·c),  h = √(δ²+4|g|²)
+                const double dl = b - a;
+                const double ig = rsqrt(g2);
+                const double rh = rsqrt(dl * dl + 4.0 * g2);
+                const double c2 = 0.5 + 0.5 * fabs(dl) * rh;
+                const double rc = rsqrt(c2);
+                s_rotp[tid][0] = c2 * rc;                                        // c
+                s_rotp[tid][1] = (dl >= 0 ? 1.0 : -1.0) * (g2 * ig) * rh * rc;   // s
+                s_rotp[tid][2] = gx * ig;                                        // e^{-iφ}
+                s_rotp[tid][3] = -gy * ig;
               }
+            }
+            if (tid < BC) s_do[tid] = rotate ? 1 : 0;
+            const unsigned any = __ballot_sync(0xffffffffu, rotate);
+            if (tid == 0) { s_anyrot = any != 0; if (any) s_rot = 1; }
+          }
+          __syncthreads();
+          if (!s_anyrot) continue;  // converged pairs only: the columns are untouched
+          // ---- phase C: apply the rotations to the rows still held in registers ---------------------------
+          if (live && s_do[pi]) {
+            const double c = s_rotp[pi][0], s = s_rotp[pi][1], phx = s_rotp[pi][2], phy = s_rotp[pi][3];
+#pragma unroll
+            for (int k = 0; k < RPL; ++k) {
+              const double2 x = xr[k];
+              double2 y;
+              y.x = yr[k].x * phx - yr[k].y * phy;
+              y.y = yr[k].x * phy + yr[k].y * phx;
+              double2 xn, yn;
+              xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+              yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+              if (xres) xr[k] = xn; else cp[l + LPP * k] = xn;
+              cq[l + LPP * k] = yn;
             }
           }
           __syncthreads();
         }
+        if (bt != 0 && pi < BC) {  // the resident columns go back to shared memory before the blocks are stored
+#pragma unroll
+          for (int k = 0; k < RPL; ++k) cols[pi * ld + l + LPP * k] = xr[k];
+        }
+        if (bt != 0) __syncthreads();
         if (C > 1) {
           store_blocks();
           if (bt == nb - 2 && tid == 0 && s_rot) atomicOr(&ax->rot[sweep], 1);

@@ -81,6 +81,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
   { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_CHOL"); use_chol_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_DMMA"); use_dmma_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_CLUSTER_JACOBI"); use_cluster_jacobi_ = !(e && e[0] == '0'); }
   cudaMemPool_t pool;
@@ -112,6 +113,7 @@ Engine::Engine(const Engine& o)
   use_tc_ = o.use_tc_;
   use_cluster_jacobi_ = o.use_cluster_jacobi_;
   use_dmma_ = o.use_dmma_;
+  use_chol_ = o.use_chol_;
   profiling_ = o.profiling_;
   comm_ = o.comm_; owner_ = o.owner_; rank_ = o.rank_; nranks_ = o.nranks_;
   TNQS_CUDA(cudaSetDevice(device_));
@@ -1443,7 +1445,31 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           jg[j].sval = (double*)talloc(sizeof(double) * n);
           jg[j].perm = (int*)talloc(sizeof(int) * n);
         }
-      if (nm > 0) {
+      int maxn_g = 0;
+      for (auto& h : ht) maxn_g = std::max(maxn_g, h.n);
+      if (nm > 0 && use_chol_ && maxn_g <= 96) {
+        // Cholesky-preconditioned eigendecomposition (kernels_small.cuh): L in shared memory, Jacobi on L without V
+        std::vector<CholTask> ct(2 * nm);
+        for (int j = 0; j < 2 * nm; ++j) {
+          ct[j].G = ht[j].G; ct[j].A = ht[j].A; ct[j].V = ht[j].V; ct[j].n = ht[j].n;
+          ct[j].piv = (int*)talloc(sizeof(int) * ht[j].n);
+          ct[j].sval = jg[j].sval;
+          jg[j].V = nullptr;
+        }
+        static bool attr_set = false;
+        if (!attr_set) {
+          TNQS_CUDA(cudaFuncSetAttribute(chol_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+          attr_set = true;
+        }
+        CholTask* dc = upload(ct);
+        const size_t sm = (size_t)maxn_g * maxn_g * sizeof(double2) + (size_t)maxn_g * (sizeof(double) + sizeof(int));
+        chol_prepare_kernel<<<2 * nm, 256, sm, stream_>>>(dc, 1e-15);
+        count_launch();
+        launch_jacobi(jg, 1e-40);  // the null columns of L are exactly zero
+        chol_finish_kernel<<<2 * nm, 256, 0, stream_>>>(dc);
+        count_launch();
+        TNQS_CUDA(cudaGetLastError());
+      } else if (nm > 0) {
         HermTask* dh = upload(ht);
         herm_prepare_kernel<<<2 * nm, 256, 0, stream_>>>(dh);
         count_launch();

@@ -121,6 +121,7 @@ class Engine {
   bool profiling_ = false;
   int wall_depth_ = 0;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
+  bool use_chol_ = true;            // Cholesky-preconditioned eigendecomposition of the reduced-factor Gram (env TNQS_CHOL=0: Jacobi on G)
   bool use_dmma_ = true;            // fp64 tensor-core Hermitian Gram (env TNQS_DMMA=0: SIMT fp64 kernel)
   bool use_cluster_jacobi_ = true;  // shared-memory cluster Jacobi (env TNQS_CLUSTER_JACOBI=0: L2-resident kernel)
   std::shared_ptr<CommHandle> comm_;  // null: single GPU

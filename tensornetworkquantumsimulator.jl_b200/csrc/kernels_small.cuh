@@ -280,6 +280,129 @@ __global__ void herm_prepare_kernel(const HermTask* __restrict__ tasks) {
   }
 }
 
+// Pivoted Cholesky of the (PSD) reduced-factor Gram matrix, the preconditioner of its Jacobi
+// eigendecomposition: with P·G·Pᵀ = L·L†, one-sided Jacobi on the columns of L gives L·W = U·Σ, hence
+// G = Pᵀ·U·Σ²·U†·P — eigenvalues σ², eigenvectors Pᵀ·U.  Jacobi on L converges in about half the sweeps it
+// needs on G itself (whose columns are graded by the eigenvalues), needs no accumulated V, and returns the
+// small eigenvalues to high relative accuracy (Veselić–Hari).  One CTA per matrix, matrix in shared memory.
+struct CholTask {
+  const double2* G;  // n×n row-major
+  double2* A;        // out: L, n×n column-major (columns ≥ rank are zero); after chol_finish: G·V = V·Σ²
+  double2* V;        // out of chol_finish: eigenvectors, n×n column-major
+  int* piv;          // [n] row i of L is row piv[i] of G
+  const double* sval;  // [n] column norms after the Jacobi (chol_finish)
+  int n;
+};
+
+__global__ void __launch_bounds__(256) chol_prepare_kernel(const CholTask* __restrict__ tasks, double tol) {
+  extern __shared__ __align__(16) unsigned char chol_raw[];
+  const CholTask t = tasks[blockIdx.x];
+  const int n = t.n, tid = threadIdx.x, nt = blockDim.x;
+  double2* S = reinterpret_cast<double2*>(chol_raw);             // [n][n] trailing matrix / L (row-major)
+  double* d = reinterpret_cast<double*>(S + (size_t)n * n);      // [n] running diagonal
+  int* piv = reinterpret_cast<int*>(d + n);                      // [n]
+  __shared__ double s_best[8];
+  __shared__ int s_besti[8];
+  __shared__ int s_p, s_stop;
+  __shared__ double s_dmax0;
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int i = idx / n, j = idx - i * n;
+    const double2 a = t.G[idx], b = t.G[(long long)j * n + i];
+    double2 h; h.x = 0.5 * (a.x + b.x); h.y = 0.5 * (a.y - b.y);
+    S[idx] = h;
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += nt) { d[i] = S[i * n + i].x; piv[i] = i; }
+  __syncthreads();
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    // ---- pivot: largest remaining diagonal entry, ties to the smallest index (deterministic) ----------
+    double best = -1.0; int besti = n;
+    for (int i = k + tid; i < n; i += nt) { const double v = d[i]; if (v > best) { best = v; besti = i; } }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+      if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+    }
+    if ((tid & 31) == 0) { s_best[tid >> 5] = best; s_besti[tid >> 5] = besti; }
+    __syncthreads();
+    if (tid == 0) {
+      double b = -1.0; int bi = n;
+      for (int w = 0; w < (nt + 31) / 32; ++w)
+        if (s_best[w] > b || (s_best[w] == b && s_besti[w] < bi)) { b = s_best[w]; bi = s_besti[w]; }
+      if (k == 0) s_dmax0 = b;
+      s_p = bi;
+      s_stop = !(b > tol * s_dmax0) || !(b > 0.0);
+    }
+    __syncthreads();
+    if (s_stop) { rank = k; break; }
+    const int p = s_p;
+    if (p != k) {  // symmetric permutation k <-> p of the trailing matrix and of the finished columns of L
+      for (int j = tid; j < n; j += nt) { const double2 a = S[k * n + j]; S[k * n + j] = S[p * n + j]; S[p * n + j] = a; }
+      __syncthreads();
+      for (int i = tid; i < n; i += nt) {
+        if (i >= k) {  // columns k, p only matter inside the trailing block (the finished part of L has columns < k)
+          const double2 a = S[i * n + k]; S[i * n + k] = S[i * n + p]; S[i * n + p] = a;
+        }
+      }
+      if (tid == 0) { const double x = d[k]; d[k] = d[p]; d[p] = x; const int q = piv[k]; piv[k] = piv[p]; piv[p] = q; }
+      __syncthreads();
+    }
+    const double lkk = sqrt(d[k]);
+    const double inv = 1.0 / lkk;
+    __syncthreads();
+    for (int i = k + tid; i < n; i += nt) {
+      double2 v = S[i * n + k];
+      if (i == k) { v.x = lkk; v.y = 0.0; } else { v.x *= inv; v.y *= inv; }
+      S[i * n + k] = v;
+    }
+    __syncthreads();
+    // trailing update S[i][j] −= L[i][k]·conj(L[j][k]) for i, j > k (both triangles: keeps the swaps trivial)
+    const int m = n - k - 1;
+    for (int idx = tid; idx < m * m; idx += nt) {
+      const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+      const double2 li = S[i * n + k], lj = S[j * n + k];
+      double2 v = S[i * n + j];
+      v.x -= li.x * lj.x + li.y * lj.y;
+      v.y -= li.y * lj.x - li.x * lj.y;
+      S[i * n + j] = v;
+      if (i == j) d[i] = v.x;
+    }
+    __syncthreads();
+  }
+  // ---- write L column-major, zero above the diagonal and beyond the rank ---------------------------------
+  for (int idx = tid; idx < n * n; idx += nt) {
+    const int j = idx / n, i = idx - j * n;  // column j, row i
+    double2 v; v.x = 0; v.y = 0;
+    if (j < rank && i >= j) v = S[i * n + j];
+    t.A[idx] = v;
+  }
+  for (int i = tid; i < n; i += nt) t.piv[i] = piv[i];
+}
+
+// after the Jacobi on L: V = Pᵀ·U (U = normalised columns), A ← V·Σ² (= G·V, what su_theta expects)
+__global__ void __launch_bounds__(256) chol_finish_kernel(const CholTask* __restrict__ tasks) {
+  const CholTask t = tasks[blockIdx.x];
+  const int n = t.n;
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int j = idx / n, i = idx - j * n;
+    const double sg = t.sval[j];
+    double2 v = t.A[idx];
+    const double f = sg > 0 ? 1.0 / sg : 0.0;
+    v.x *= f; v.y *= f;
+    t.V[(long long)j * n + t.piv[i]] = v;
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    const int j = idx / n;
+    const double sg = t.sval[j];
+    double2 v = t.V[idx];
+    v.x *= sg * sg; v.y *= sg * sg;
+    t.A[idx] = v;
+  }
+}
+
 struct SuGateTask {
   // per site: eigen-decomposition of the Gram matrix of the gauged tensor (n = d·χ_b)
   const double2* GA[2];  // G·V (column-major) after Jacobi

@@ -225,7 +225,8 @@ def run_ours(args):
     h2d = int(nverts.nbytes + verts.nbytes + mats.nbytes)
     psi.stats(reset=True)
     sampler = ClockSampler(local)
-    sampler.start()
+    if not args.no_sampler:
+        sampler.start()
     sweeps, e2e_s, dev_ms, zs = 0, 0.0, 0.0, []
     maxerr = 0.0
     st = {"bp_ms": 0.0, "su_ms": 0.0, "bp_sweeps": 0, "kernel_launches": 0}
@@ -235,13 +236,13 @@ def run_ours(args):
     t_region = time.perf_counter()
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)  # public API, host in/out
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=args.inplace)  # public API, host in/out
         z = tq.expect(psi, obs)
         e2e_s += time.perf_counter() - t0
         zs.append(float(np.real(z)))
         maxerr = max(maxerr, float(errs.max()))
         sweeps += sum(r["niter"] for r in psi.last_bp_reports)
-        s1 = psi.stats()  # the returned cache is a fresh clone: its counters cover exactly this call
+        s1 = psi.stats(reset=args.inplace)  # the returned cache is a fresh clone: its counters cover exactly this call
         for k in st:
             st[k] += s1[k]
     sync_all()
@@ -329,6 +330,8 @@ def main():
     ap.add_argument("--prep", type=int, default=15, help="untimed layers from the product state before warm-up")
     ap.add_argument("--schedule", default="bipartite", choices=["bipartite", "forest"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--inplace", action="store_true", help="diagnostic: mutate the cache instead of the reference's functional copy")
+    ap.add_argument("--no-sampler", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region")
     ap.add_argument("--cuda-profiler", action="store_true", help="cudaProfilerStart/Stop around the timed steps (for ncu --profile-from-start off)")
     ap.add_argument("--ref-budget", type=float, default=20.0)
     ap.add_argument("--ref-bp-sweeps", type=float, default=15.0)

@@ -36,6 +36,45 @@ struct UpPool {
     free_[device].push_back({d, h});
   }
 };
+struct SlabPool {
+  std::mutex mu;
+  std::map<int, std::vector<std::pair<char*, size_t>>> free_;
+  static SlabPool& get() { static SlabPool p; return p; }
+  std::pair<char*, size_t> take(int device, size_t bytes) {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      auto& v = free_[device];
+      int best = -1;
+      for (int i = 0; i < (int)v.size(); ++i)
+        if (v[i].second >= bytes && (best < 0 || v[i].second < v[best].second)) best = i;
+      if (best >= 0) { auto c = v[best]; v.erase(v.begin() + best); return c; }
+    }
+    char* d = nullptr;
+    if (cudaMalloc(&d, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      trim(device);  // give cached slabs and the idle part of the stream-ordered pool back to the driver, retry once
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+      if (cudaMalloc(&d, bytes) != cudaSuccess) throw Error(TNQS_ECUDA, "cudaMalloc(scratch slab) failed: out of device memory");
+    }
+    return {d, bytes};
+  }
+  void give(int device, char* d, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_[device].push_back({d, bytes});
+  }
+  size_t free_bytes(int device) {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t t = 0;
+    for (auto& c : free_[device]) t += c.second;
+    return t;
+  }
+  void trim(int device) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& c : free_[device]) cudaFree(c.first);
+    free_[device].clear();
+  }
+};
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -81,6 +120,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
   { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_FAST_SVD"); use_fast_svd_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_CHOL"); use_chol_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_DMMA"); use_dmma_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_CLUSTER_JACOBI"); use_cluster_jacobi_ = !(e && e[0] == '0'); }
@@ -114,6 +154,7 @@ Engine::Engine(const Engine& o)
   use_cluster_jacobi_ = o.use_cluster_jacobi_;
   use_dmma_ = o.use_dmma_;
   use_chol_ = o.use_chol_;
+  use_fast_svd_ = o.use_fast_svd_;
   profiling_ = o.profiling_;
   comm_ = o.comm_; owner_ = o.owner_; rank_ = o.rank_; nranks_ = o.nranks_;
   TNQS_CUDA(cudaSetDevice(device_));
@@ -147,6 +188,8 @@ Engine::~Engine() {
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : temps_) cudaFreeAsync(p, stream_);
   for (char* p : arena_) cudaFreeAsync(p, stream_);
+  for (auto& sl : slabs_) SlabPool::get().give(device_, sl.first, sl.second);
+  slabs_.clear();
   for (auto& s : up_) {  // the stream is idle: the chunks can serve another engine
     for (auto& c : s.chunks) UpPool::get().give(device_, c.dev, c.host);
     s.chunks.clear();
@@ -172,10 +215,23 @@ void* Engine::dalloc(size_t bytes) {
 // Temporaries: small ones are bump-allocated from cached 32 MiB chunks (thousands per gate batch —
 // one cudaMallocAsync each would dominate the host time), large ones go to the stream-ordered pool.
 void* Engine::talloc(size_t bytes) {
-  constexpr size_t kChunk = 32ull << 20, kSmall = 1ull << 20;
+  constexpr size_t kChunk = 32ull << 20, kSmall = 1ull << 20, kSlab = 1ull << 30;
   if (bytes >= kSmall) {
-    void* p = dalloc(bytes);
-    temps_.push_back(p);
+    // tensor-sized temporaries are carved from 1 GiB slabs: a BP level needs ~10³ of them and one
+    // cudaMallocAsync + cudaFreeAsync per buffer made the host the bottleneck of the sweep
+    // The slabs come from a process-wide cache (cudaMalloc once, reused by every engine and clone): the
+    // stream-ordered pool cannot coalesce its free blocks into GiB-sized ones and would keep mapping new memory.
+    bytes = (bytes + 255) & ~size_t(255);
+    while (true) {
+      if (slab_cur_ < slabs_.size() && slab_off_ + bytes <= slabs_[slab_cur_].second) break;
+      if (slab_cur_ < slabs_.size()) { ++slab_cur_; slab_off_ = 0; }
+      if (slab_cur_ >= slabs_.size()) {
+        slabs_.push_back(SlabPool::get().take(device_, std::max(kSlab, bytes)));
+        slab_off_ = 0;
+      }
+    }
+    void* p = slabs_[slab_cur_].first + slab_off_;
+    slab_off_ += bytes;
     return p;
   }
   bytes = (bytes + 255) & ~size_t(255);
@@ -195,6 +251,7 @@ void Engine::dfree(void* p) {
 void Engine::free_temps() {
   for (void* p : temps_) TNQS_CUDA(cudaFreeAsync(p, stream_));
   temps_.clear();
+  slab_cur_ = 0; slab_off_ = 0;  // slabs stay with the engine until it is destroyed
   arena_cur_ = 0;  // chunks stay cached; reuse is ordered by the single engine stream
   arena_off_ = 0;
   // close the upload epoch: its pinned mirrors may be rewritten only after the copies queued so far ran
@@ -301,7 +358,9 @@ size_t Engine::scratch_budget() const {
     cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
     cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
   }
-  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0);
+  size_t mine = 0;
+  for (auto& sl : slabs_) mine += sl.second;
+  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0) + SlabPool::get().free_bytes(device_) + mine;
   return (size_t)(0.7 * (double)avail);
 }
 
@@ -1454,6 +1513,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           ct[j].G = ht[j].G; ct[j].A = ht[j].A; ct[j].V = ht[j].V; ct[j].n = ht[j].n;
           ct[j].piv = (int*)talloc(sizeof(int) * ht[j].n);
           ct[j].sval = jg[j].sval;
+          ct[j].scratch = nullptr;
           jg[j].V = nullptr;
         }
         static bool attr_set = false;
@@ -1506,6 +1566,52 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         ds = upload(stm);
         su_theta_kernel<<<nm, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
         count_launch();
+        // Preconditioned SVD: K = θ†θ → pivoted Cholesky P·K·Pᵀ = L·L† → Jacobi on L (fast: L is the
+        // preconditioned form, and only rank(θ) columns are non-zero) → V_K = Pᵀ·U_L ≈ right singular vectors →
+        // B = θ·V_K has nearly orthogonal columns → a short Jacobi polish on B restores full relative accuracy.
+        // Directions with σ < ~3e-8·σmax (σ² below the fp64 noise of K) come back as σ = 0, so the path is taken
+        // only when they cannot matter: ComplexF32 states (fp32 noise 6e-8) or a relative cutoff ≥ 1e-14 on σ².
+        int maxcols_t = 0, maxrows_t = 0;
+        for (auto& j : jt) { maxcols_t = std::max(maxcols_t, j.n); maxrows_t = std::max(maxrows_t, j.m); }
+        if (use_fast_svd_ && (c64() || ao.cutoff >= 1e-14) && maxcols_t <= 256 && maxrows_t <= 256 && maxcols_t >= 8) {
+          std::vector<CholTask> ct(nm);
+          std::vector<SmallGemmTask> g1(nm), g2(nm);
+          std::vector<JacobiTask> jl(nm);
+          const bool glob = maxcols_t > 96;
+          for (int q = 0; q < nm; ++q) {
+            const int k = mine[q];
+            const int rows = jt[q].m, cols = jt[q].n;
+            double2* K = (double2*)talloc((size_t)cols * cols * sizeof(double2));
+            double2* L = (double2*)talloc((size_t)cols * cols * sizeof(double2));
+            double2* Vk = (double2*)talloc((size_t)cols * cols * sizeof(double2));
+            ct[q].G = K; ct[q].A = L; ct[q].V = Vk; ct[q].n = cols;
+            ct[q].piv = (int*)talloc(sizeof(int) * cols);
+            double* sv1 = (double*)talloc(sizeof(double) * cols);
+            ct[q].sval = sv1;
+            ct[q].scratch = glob ? (double2*)talloc((size_t)cols * cols * sizeof(double2)) : nullptr;
+            g1[q].A = st[k].theta; g1[q].B = nullptr; g1[q].out = K; g1[q].m = rows; g1[q].n = cols;
+            g2[q].A = st[k].theta0; g2[q].B = Vk; g2[q].out = st[k].theta; g2[q].m = rows; g2[q].n = cols;
+            jl[q].A = L; jl[q].V = nullptr; jl[q].m = cols; jl[q].n = cols; jl[q].sval = sv1;
+            jl[q].perm = (int*)talloc(sizeof(int) * cols);
+          }
+          static bool attr_set2 = false;
+          if (!attr_set2) {
+            TNQS_CUDA(cudaFuncSetAttribute(chol_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+            attr_set2 = true;
+          }
+          SmallGemmTask* d1 = upload(g1);
+          SmallGemmTask* d2 = upload(g2);
+          CholTask* dc = upload(ct);
+          colgram_kernel<<<nm, 256, 0, stream_>>>(d1);
+          const size_t sm = (glob ? 0 : (size_t)maxcols_t * maxcols_t * sizeof(double2)) + (size_t)maxcols_t * (sizeof(double) + sizeof(int));
+          chol_prepare_kernel<<<nm, 256, sm, stream_>>>(dc, 1e-15);
+          count_launch(2);
+          launch_jacobi(jl, 1e-40);
+          chol_finish_kernel<<<nm, 256, 0, stream_>>>(dc);
+          colapply_kernel<<<nm, 256, 0, stream_>>>(d2);
+          count_launch(2);
+          TNQS_CUDA(cudaGetLastError());
+        }
         // singular values below 1e-13·‖θ‖_F never survive the truncation (σ² < 1e-26 of the total weight)
         launch_jacobi(jt, 1e-26);
         su_truncate_kernel<<<(nm + 63) / 64, 64, 0, stream_>>>(ds, nm, ao.maxdim, ao.mindim, ao.cutoff);

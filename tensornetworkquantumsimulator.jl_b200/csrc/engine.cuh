@@ -104,6 +104,8 @@ class Engine {
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   std::vector<void*> temps_;    // stream-ordered temporaries freed by free_temps()
+  std::vector<std::pair<char*, size_t>> slabs_;  // GiB-sized scratch slabs for tensor-sized temporaries (process-wide cache)
+  size_t slab_cur_ = 0, slab_off_ = 0;
   std::vector<char*> arena_;    // cached chunks for small temporaries
   size_t arena_cur_ = 0, arena_off_ = 0;
   // Task tables go host→device through a ring of (device, pinned-host mirror) chunks so that the
@@ -121,6 +123,7 @@ class Engine {
   bool profiling_ = false;
   int wall_depth_ = 0;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
+  bool use_fast_svd_ = true;        // Cholesky-preconditioned θ-SVD with Jacobi polish (env TNQS_FAST_SVD=0: plain Jacobi on θ)
   bool use_chol_ = true;            // Cholesky-preconditioned eigendecomposition of the reduced-factor Gram (env TNQS_CHOL=0: Jacobi on G)
   bool use_dmma_ = true;            // fp64 tensor-core Hermitian Gram (env TNQS_DMMA=0: SIMT fp64 kernel)
   bool use_cluster_jacobi_ = true;  // shared-memory cluster Jacobi (env TNQS_CLUSTER_JACOBI=0: L2-resident kernel)

@@ -292,14 +292,16 @@ struct CholTask {
   int* piv;          // [n] row i of L is row piv[i] of G
   const double* sval;  // [n] column norms after the Jacobi (chol_finish)
   int n;
+  double2* scratch;  // n×n global work matrix when the matrix does not fit shared memory, else nullptr
 };
 
 __global__ void __launch_bounds__(256) chol_prepare_kernel(const CholTask* __restrict__ tasks, double tol) {
   extern __shared__ __align__(16) unsigned char chol_raw[];
   const CholTask t = tasks[blockIdx.x];
   const int n = t.n, tid = threadIdx.x, nt = blockDim.x;
-  double2* S = reinterpret_cast<double2*>(chol_raw);             // [n][n] trailing matrix / L (row-major)
-  double* d = reinterpret_cast<double*>(S + (size_t)n * n);      // [n] running diagonal
+  // [n][n] trailing matrix / L (row-major): shared memory, or the task's global scratch (L2-resident) for large n
+  double2* S = t.scratch ? t.scratch : reinterpret_cast<double2*>(chol_raw);
+  double* d = reinterpret_cast<double*>(chol_raw + (t.scratch ? 0 : (size_t)n * n * sizeof(double2)));  // [n] running diagonal
   int* piv = reinterpret_cast<int*>(d + n);                      // [n]
   __shared__ double s_best[8];
   __shared__ int s_besti[8];
@@ -400,6 +402,92 @@ __global__ void __launch_bounds__(256) chol_finish_kernel(const CholTask* __rest
     double2 v = t.V[idx];
     v.x *= sg * sg; v.y *= sg * sg;
     t.A[idx] = v;
+  }
+}
+
+// K = A†·A for an m×n column-major A (the θ of a gate), row-major n×n out — Gram of the θ columns
+struct SmallGemmTask {
+  const double2* A;   // m×n column-major
+  const double2* B;   // n×n column-major (apply) or unused
+  double2* out;
+  int m, n;
+};
+__global__ void __launch_bounds__(256) colgram_kernel(const SmallGemmTask* __restrict__ tasks) {
+  const SmallGemmTask t = tasks[blockIdx.x];
+  const int m = t.m, n = t.n;
+  // 4×4 register tiles over the lower triangle of the n×n result
+  const int nt4 = (n + 3) / 4;
+  for (int tile = threadIdx.x; tile < nt4 * nt4; tile += blockDim.x) {
+    const int ti = tile / nt4, tj = tile - ti * nt4;
+    if (tj > ti) continue;
+    double2 acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { acc[a][b].x = 0; acc[a][b].y = 0; }
+    for (int k = 0; k < m; ++k) {
+      double2 x[4], y[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * ti + a, j = 4 * tj + a;
+        x[a] = i < n ? t.A[(long long)i * m + k] : make_double2(0, 0);
+        y[a] = j < n ? t.A[(long long)j * m + k] : make_double2(0, 0);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {  // conj(x_a)·y_b
+          acc[a][b].x += x[a].x * y[b].x + x[a].y * y[b].y;
+          acc[a][b].y += x[a].x * y[b].y - x[a].y * y[b].x;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * ti + a, j = 4 * tj + b;
+        if (i < n && j < n) {
+          t.out[(long long)i * n + j] = acc[a][b];
+          if (ti != tj) { double2 c = acc[a][b]; c.y = -c.y; t.out[(long long)j * n + i] = c; }
+        }
+      }
+  }
+}
+// out = A·B : (m×n)·(n×n), all column-major — θ times the approximate right singular vectors
+__global__ void __launch_bounds__(256) colapply_kernel(const SmallGemmTask* __restrict__ tasks) {
+  const SmallGemmTask t = tasks[blockIdx.x];
+  const int m = t.m, n = t.n;
+  const int mt4 = (m + 3) / 4, nt4 = (n + 3) / 4;
+  for (int tile = threadIdx.x; tile < mt4 * nt4; tile += blockDim.x) {
+    const int tj = tile / mt4, ti = tile - tj * mt4;  // consecutive threads → consecutive row tiles
+    double2 acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) { acc[a][b].x = 0; acc[a][b].y = 0; }
+    for (int k = 0; k < n; ++k) {
+      double2 x[4], y[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int i = 4 * ti + a, j = 4 * tj + a;
+        x[a] = i < m ? t.A[(long long)k * m + i] : make_double2(0, 0);
+        y[a] = j < n ? t.B[(long long)j * n + k] : make_double2(0, 0);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          acc[a][b].x += x[a].x * y[b].x - x[a].y * y[b].y;
+          acc[a][b].y += x[a].x * y[b].y + x[a].y * y[b].x;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * ti + a, j = 4 * tj + b;
+        if (i < m && j < n) t.out[(long long)j * m + i] = acc[a][b];
+      }
   }
 }
 

@@ -160,6 +160,8 @@ typedef struct {
   double  mode_bytes, gram_bytes;     /* algorithmic HBM bytes: tensors read + written once        */
   double  wall_ms;                    /* host wall time spent inside tnqs_apply_gates / tnqs_bp_update
                                          (device time bp_ms + su_ms below it means the host is the limit) */
+  double  sync_ms;                    /* part of wall_ms the host spent blocked waiting for the device;
+                                         wall_ms - sync_ms = host preparation / enqueue time               */
 } tnqs_stats;
 int  tnqs_get_stats(tnqs_handle h, tnqs_stats* out, int reset);
 int  tnqs_set_profiling(tnqs_handle h, int on);

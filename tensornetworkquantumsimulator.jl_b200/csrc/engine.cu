@@ -13,6 +13,13 @@ namespace tnqs {
 
 using cplx = std::complex<double>;
 
+// host time spent blocked on the device (stats: wall_ms − sync_ms = host time spent preparing / enqueueing)
+struct WaitScope {
+  double* acc; std::chrono::steady_clock::time_point t0;
+  explicit WaitScope(double* a) : acc(a), t0(std::chrono::steady_clock::now()) {}
+  ~WaitScope() { *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 // Process-wide free list of upload chunks per device: apply_gates / update clone the engine for the
 // reference's functional-copy semantics, and pinning host memory (cudaHostAlloc) costs milliseconds.
 namespace {
@@ -262,7 +269,7 @@ void Engine::free_temps() {
     s.pending = true;
     up_cur_ = (up_cur_ + 1) % kUpSets;
     UpSet& n = up_[up_cur_];
-    if (n.pending) { TNQS_CUDA(cudaEventSynchronize(n.done)); n.pending = false; }
+    if (n.pending) { { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaEventSynchronize(n.done)); } n.pending = false; }
     n.cur = 0; n.off = 0;
   }
 }
@@ -732,8 +739,9 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
     for (int g = 0; g < 2; ++g) {
       if (tt[g].empty()) continue;
       const unsigned scols = g ? 32 : 16;
-      // aim at ~8 CTAs per SM overall, at least 512 columns per split
-      const long long target_cols = std::max<long long>(512, work[g] / (148 * 8));
+      // K-steps are interleaved over the CTAs of a task (kernels_tc.cuh): many splits per task keep the CTAs
+      // that run together on neighbouring DRAM pages; ≥ 2048 columns (≥ 64 steps) per CTA amortise the epilogue
+      const long long target_cols = std::max<long long>(2048, work[g] / (148 * 64));
       std::vector<int> cta_task;
       int ncta = 0;
       for (size_t k = 0; k < tt[g].size(); ++k) {
@@ -1250,7 +1258,7 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
     if (use_tol) {
       allreduce_sum(d_diff, nseq);
       TNQS_CUDA(cudaMemcpyAsync(h_diff.data(), d_diff, sizeof(double) * nseq, cudaMemcpyDeviceToHost, stream_));
-      TNQS_CUDA(cudaStreamSynchronize(stream_));
+      { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaStreamSynchronize(stream_)); }
       double s = 0;
       for (double x : h_diff) s += x;
       rep.diff = s / nseq;
@@ -1259,7 +1267,7 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
   }
   dfree(d_diff);
   TNQS_CUDA(cudaEventRecord(t1, stream_));
-  TNQS_CUDA(cudaEventSynchronize(t1));
+  { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaEventSynchronize(t1)); }
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
   stats_.bp_ms += ms;
@@ -1631,7 +1639,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       TNQS_CUDA(cudaMemcpyAsync(h_rec.data(), d_rec, h_rec.size(), cudaMemcpyDeviceToHost, stream_));
       if (!mt.empty())
         TNQS_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * 2 * mt.size(), cudaMemcpyDeviceToHost, stream_));
-      TNQS_CUDA(cudaStreamSynchronize(stream_));
+      { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaStreamSynchronize(stream_)); }
       for (int k = 0; k < ng; ++k) {
         const char* rec = h_rec.data() + rec_bytes * (size_t)slot(k);
         std::memcpy(&err[k], rec, sizeof(double));
@@ -1845,7 +1853,7 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
   }
   if (n_reports) *n_reports = nrep;
   TNQS_CUDA(cudaEventRecord(t1, stream_));
-  TNQS_CUDA(cudaEventSynchronize(t1));
+  { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaEventSynchronize(t1)); }
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
   stats_.su_ms += ms - (stats_.bp_ms - bp_before);

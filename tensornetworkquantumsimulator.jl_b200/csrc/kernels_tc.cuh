@@ -252,15 +252,18 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
   uint32_t phase = 0;
   bool b_ready = false;
 
+  // tiles are dealt round-robin to the CTAs of a task (tile = cta_local + i·ncta): CTAs resident together
+  // stream neighbouring 512-byte pieces of the same tensor rows (same DRAM pages)
   const int cta_local = blockIdx.x - t.cta_begin;
-  const int tile0 = cta_local * t.tiles_per_cta;
-  const int tile1 = min(t.ntiles, tile0 + t.tiles_per_cta);
+  const int ncta_task = (t.ntiles + t.tiles_per_cta - 1) / t.tiles_per_cta;
+  const int tile0 = cta_local;
+  const int tile1 = t.ntiles;
   constexpr int COLS = LAST ? 128 : 64;  // complex columns per tile
 
   float4 xr[4];
   if (tile0 < tile1) tc_load_tile<LAST>(t, 0, (unsigned)tile0 * COLS, tid, xr);
 
-  for (int tile = tile0; tile < tile1; ++tile) {
+  for (int tile = tile0; tile < tile1; tile += ncta_task) {
     const unsigned c0 = (unsigned)tile * COLS;
     for (int ch = 0; ch < t.nchunk; ++ch) {
       tc_store_stage<LAST>(tid, xr, sAh, sAl);
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_mode_kernel(const TcModeTask* _
       // prefetch the next chunk / tile into registers while this one is multiplied
       {
         int nch = ch + 1, ntile = tile;
-        if (nch == t.nchunk) { nch = 0; ntile = tile + 1; }
+        if (nch == t.nchunk) { nch = 0; ntile = tile + ncta_task; }
         if (ntile < tile1) tc_load_tile<LAST>(t, nch, (unsigned)ntile * COLS, tid, xr);
       }
       if (!b_ready) { mbar_wait(smem_u32(&s_bar_b), 0); b_ready = true; }
@@ -450,10 +453,13 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* _
   const uint32_t tmem = s_tmem;
   const uint32_t idesc = make_idesc(t.MMp, t.NNp, LAST ? 1 : 0, LAST ? 1 : 0);
 
-  const unsigned cb = (unsigned)split * t.cols_per_split;
-  const unsigned ce = min(t.CC, cb + t.cols_per_split);
+  // K-steps are dealt round-robin to the nsplit CTAs of a task (step s of this CTA = global step
+  // s·nsplit + split): CTAs that are resident together then read neighbouring 128-byte pieces of the same
+  // tensor rows, i.e. the same DRAM pages, instead of nsplit·2χ far-apart sequential streams per task.
   constexpr int SCOLS = LAST ? 32 : 16;  // complex columns per stage (KC real K either way)
-  const int nstage = (int)((ce - cb + SCOLS - 1) / SCOLS);
+  const unsigned ce = t.CC;
+  const int total_steps = (int)((t.CC + SCOLS - 1) / SCOLS);
+  const int nstage = split < total_steps ? (total_steps - split + t.nsplit - 1) / t.nsplit : 0;
   uint32_t ph[2] = {0, 0};
   int used[2] = {0, 0};
 
@@ -487,9 +493,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* _
 
   float4 rx[PD][NIT], ry[PD][NIT];
   auto load_stage = [&](int st, float4 (&x)[NIT], float4 (&y)[NIT]) {
-    const unsigned k0 = cb + (unsigned)st * SCOLS;
+    const unsigned k0 = ((unsigned)st * (unsigned)t.nsplit + (unsigned)split) * SCOLS;
     if (!LAST) {
-      // 16 complex columns of one outer slice (inner % 16 == 0 and the split starts on a multiple of 16)
+      // 16 complex columns of one outer slice (inner % 16 == 0 and every step starts on a multiple of 16)
       const unsigned o = k0 / t.inner, n0 = k0 - o * t.inner;
       const int nvalid = (int)min((unsigned)SCOLS, ce - k0);  // multiple of 2 by construction
       const long long base = (long long)o * chi * t.inner + n0;

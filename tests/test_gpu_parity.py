@@ -269,3 +269,82 @@ def test_tensor_core_mode_products(chi):
     zs = tq.expect(out2, [("Z", [a]), ("Z", [b])])
     zo = [orc.expect_local(c3, g.index[a], Z), orc.expect_local(c3, g.index[b], Z)]
     assert np.max(np.abs(np.array(zs) - np.array(zo))) < 1e-4
+
+
+def _evolve(dtype, g, layer, seq, kw, nlayers, env):
+    """Run `nlayers` layers with the engine's kernel-selection environment variables set to `env`
+    (they are read when a cache is created)."""
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        psi = tq.BeliefPropagationCache(tq.zerostate(dtype, g))
+        bp = dict(maxiter=100, tolerance=1e-12 if dtype == np.complex128 else 1e-9, edge_sequence=seq)
+        errs_all = []
+        for _ in range(nlayers):
+            psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)
+            errs_all.append(errs)
+        zs = np.array(tq.expect(psi, [("Z", [v]) for v in g.vertices()]))
+        return zs, np.concatenate(errs_all), list(psi.bond_dims())
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.complex128, 1e-9), (np.complex64, 2e-4)])
+@pytest.mark.parametrize("variant", [{"TNQS_FAST_SVD": "0"}, {"TNQS_CHOL": "0"}, {"TNQS_DMMA": "0"},
+                                     {"TNQS_CLUSTER_JACOBI": "0", "TNQS_FAST_SVD": "0", "TNQS_CHOL": "0"}])
+def test_kernel_variants_agree(dtype, tol, variant):
+    """The accelerated factorisation paths (Cholesky-preconditioned θ-SVD with Jacobi polish,
+    Cholesky-preconditioned eigendecomposition of the reduced-factor Gram, fp64 tensor-core Gram,
+    shared-memory cluster Jacobi) against the plain ones they replace: same truncation errors, bond
+    dimensions and ⟨Z⟩ on a truncating 4×4 TFIM evolution (bond dimension up to 8 ⇒ θ is 32×32)."""
+    g = tq.named_grid((4, 4))
+    layer = tfim_layer(g)
+    seq = tq.bipartite_edge_sequence(g)
+    kw = dict(maxdim=8, cutoff=1e-12, normalize_tensors=True)
+    base = {"TNQS_FAST_SVD": "1", "TNQS_CHOL": "1", "TNQS_DMMA": "1", "TNQS_CLUSTER_JACOBI": "1"}
+    z0, e0, b0 = _evolve(dtype, g, layer, seq, kw, 5, base)
+    z1, e1, b1 = _evolve(dtype, g, layer, seq, kw, 5, {**base, **variant})
+    assert b0 == b1
+    assert max(b0) == 8
+    assert np.max(np.abs(z0 - z1)) < tol
+    assert np.max(np.abs(e0 - e1)) < tol * max(1.0, float(np.max(e1)) / 1e-3)
+
+
+@pytest.mark.parametrize("name", ["heavy_hex", "cubic_periodic"])
+def test_other_lattices_match_oracle(name):
+    """BASELINE configs 3 and 4 at oracle-sized bond dimension: the IBM-Eagle heavy-hex graph
+    (degrees 1–3, 3 edge colours, kicked-Ising layer of examples/heavyhexIsing_dynamics.jl:12-26) and
+    a periodic cubic lattice (degree 6, layer of examples/3dIsing_dynamics.jl:15-26), complex128."""
+    if name == "heavy_hex":
+        g = tq.eagle_heavy_hex()
+        layer = [("Rx", [v], 0.4) for v in g.vertices()]
+        for grp in tq.edge_color(g, 3):
+            layer += [("Rzz", list(p), np.pi / 2) for p in grp]
+        kw = dict(maxdim=4, cutoff=1e-12, normalize_tensors=True)
+        nl, probe = 3, g.vertices()[:12]
+    else:
+        g = tq.named_grid((2, 2, 3), periodic=False)
+        layer = [("Rz", [v], -0.04) for v in g.vertices()]
+        for grp in tq.edge_color(g, 6):
+            layer += [("Rxx", list(p), -0.08) for p in grp]
+        layer += [("Rz", [v], -0.04) for v in g.vertices()]
+        kw = dict(maxdim=2, cutoff=1e-10, normalize_tensors=True)
+        nl, probe = 2, g.vertices()
+    seq = tq.bipartite_edge_sequence(g)
+    bp = dict(maxiter=200, tolerance=1e-13, edge_sequence=seq)
+    psi = tq.BeliefPropagationCache(tq.zerostate(np.complex128, g))
+    c = orc.product_state(g.nv, g.edge_uv(), [(1.0, 0.0)] * g.nv, np.complex128)
+    gm, gv = circuit_for_oracle(g, layer)
+    for _ in range(nl):
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp)
+        c, oerrs, _ = orc.apply_gates(c, gm, gv, seq_idx(g, seq), kw, dict(maxiter=200, tolerance=1e-13))
+        assert list(psi.bond_dims()) == c.bond_dims()
+        assert np.max(np.abs(errs - oerrs)) < 1e-9 * max(1.0, float(np.max(oerrs)) / 1e-3)
+    zs = np.array(tq.expect(psi, [("Z", [v]) for v in probe]))
+    zo = np.array([orc.expect_local(c, g.index[v], Z) for v in probe])
+    assert np.max(np.abs(zs - zo)) < 1e-8

@@ -22,8 +22,8 @@ fam = ["mode_ms", "gram_ms", "small_ms", "mode_launches", "gram_launches", "kern
 
 
 def show(tag, t0, t1, st):
-    print("%-34s wall %7.1f ms | lib wall %7.1f dev bp %7.1f su %7.1f | mode %6.1f gram %6.1f small %6.1f | launches %d" % (
-        tag, (t1 - t0) * 1e3, st["wall_ms"], st["bp_ms"], st["su_ms"], st["mode_ms"], st["gram_ms"], st["small_ms"], st["kernel_launches"]))
+    print("%-34s wall %7.1f ms | lib wall %7.1f (host busy %6.1f) dev bp %7.1f su %7.1f | mode %6.1f gram %6.1f small %6.1f | launches %d" % (
+        tag, (t1 - t0) * 1e3, st["wall_ms"], st["wall_ms"] - st["sync_ms"], st["bp_ms"], st["su_ms"], st["mode_ms"], st["gram_ms"], st["small_ms"], st["kernel_launches"]))
 
 
 for rep in range(2):

@@ -13,6 +13,18 @@ namespace tnqs {
 
 using cplx = std::complex<double>;
 
+// TNQS_SLOWLOG=1: report host-side CUDA calls that take longer than 3 ms (allocator / driver stalls)
+struct SlowLog {
+  const char* what; std::chrono::steady_clock::time_point t0;
+  static bool on() { static const bool v = std::getenv("TNQS_SLOWLOG") != nullptr; return v; }
+  explicit SlowLog(const char* w) : what(w), t0(std::chrono::steady_clock::now()) {}
+  ~SlowLog() {
+    if (!on()) return;
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (ms > 3.0) std::fprintf(stderr, "[tnqs slow] %s took %.1f ms\n", what, ms);
+  }
+};
+
 // host time spent blocked on the device (stats: wall_ms − sync_ms = host time spent preparing / enqueueing)
 struct WaitScope {
   double* acc; std::chrono::steady_clock::time_point t0;
@@ -34,6 +46,7 @@ struct UpPool {
       if (!v.empty()) { auto c = v.back(); v.pop_back(); return c; }
     }
     char *d = nullptr, *h = nullptr;
+    SlowLog sl("cudaMalloc+cudaHostAlloc(upload chunk)");
     if (cudaMalloc(&d, bytes) != cudaSuccess) throw Error(TNQS_ECUDA, "cudaMalloc(upload chunk) failed");
     if (cudaHostAlloc(&h, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaFree(d); throw Error(TNQS_ECUDA, "cudaHostAlloc(upload chunk) failed"); }
     return {d, h};
@@ -57,6 +70,7 @@ struct SlabPool {
       if (best >= 0) { auto c = v[best]; v.erase(v.begin() + best); return c; }
     }
     char* d = nullptr;
+    SlowLog sl("cudaMalloc(slab)");
     if (cudaMalloc(&d, bytes) != cudaSuccess) {
       cudaGetLastError();
       trim(device);  // give cached slabs and the idle part of the stream-ordered pool back to the driver, retry once
@@ -216,6 +230,7 @@ Engine::~Engine() {
 void* Engine::dalloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
+  SlowLog sl("cudaMallocAsync");
   TNQS_CUDA(cudaMallocAsync(&p, bytes, stream_));
   return p;
 }
@@ -252,7 +267,14 @@ void* Engine::talloc(size_t bytes) {
   arena_off_ += bytes;
   return p;
 }
+// hand the scratch slabs back to the process-wide cache; only when the stream has drained
+void Engine::release_slabs() {
+  for (auto& sl : slabs_) SlabPool::get().give(device_, sl.first, sl.second);
+  slabs_.clear();
+  slab_cur_ = 0; slab_off_ = 0;
+}
 void Engine::dfree(void* p) {
+  SlowLog sl("cudaFreeAsync");
   if (p) TNQS_CUDA(cudaFreeAsync(p, stream_));
 }
 void Engine::free_temps() {
@@ -298,6 +320,7 @@ template <class T> T* Engine::upload(const std::vector<T>& v) {
   if (v.empty()) return d;
   const void* src = v.data();
   if (h) { std::memcpy(h, v.data(), v.size() * sizeof(T)); src = h; }
+  SlowLog sl("cudaMemcpyAsync(upload)");
   TNQS_CUDA(cudaMemcpyAsync(d, src, v.size() * sizeof(T), cudaMemcpyHostToDevice, stream_));
   return d;
 }
@@ -356,9 +379,17 @@ void Engine::materialize_message(int de) {
   else diag_fill_kernel<double><<<dim3(nb, 1), 256, 0, stream_>>>(d);
   count_launch();
 }
-size_t Engine::scratch_budget() const {
+// `need` = bytes of tensor-sized temporaries the caller is about to carve.  When they fit the scratch slabs this
+// process already holds, no driver query is made: cudaMemGetInfo was measured to stall 10–70 ms sporadically
+// (tools/jitter_probe.py), several times per Trotter layer.
+size_t Engine::scratch_budget(size_t need) const {
+  {
+    size_t have = SlabPool::get().free_bytes(device_);
+    for (auto& sl : slabs_) have += sl.second;
+    if (need > 0 && need + need / 8 + (64ull << 20) <= have) return have;
+  }
   size_t fr = 0, tot = 0;
-  cudaMemGetInfo(&fr, &tot);
+  { SlowLog sl("cudaMemGetInfo"); cudaMemGetInfo(&fr, &tot); }
   cudaMemPool_t pool;
   uint64_t reserved = 0, used = 0;
   if (cudaDeviceGetDefaultMemPool(&pool, device_) == cudaSuccess) {
@@ -504,8 +535,8 @@ void Engine::allreduce_sum(double* dptr, size_t count) {
 }
 
 // scratch budget every rank agrees on (chunk boundaries of a gate batch carry a collective)
-size_t Engine::agreed_budget() {
-  double b = (double)scratch_budget();
+size_t Engine::agreed_budget(size_t need) {
+  double b = (double)scratch_budget(need);
   if (nranks_ <= 1) return (size_t)b;
   double* d = (double*)talloc(sizeof(double));
   TNQS_CUDA(cudaMemcpyAsync(d, &b, sizeof(double), cudaMemcpyHostToDevice, stream_));
@@ -766,12 +797,12 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       int maxchi = 0;
       for (auto& t : tt[g]) maxchi = std::max(maxchi, t.chi);
       if (g == 0) {
-        if (maxchi <= 32) tc::tc_gram_kernel<false, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else tc::tc_gram_kernel<false, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        if (maxchi <= 32) tc::tc_gram_kernel<false, 1, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<false, 2, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
       } else {
-        if (maxchi <= 16) tc::tc_gram_kernel<true, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else if (maxchi <= 32) tc::tc_gram_kernel<true, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else tc::tc_gram_kernel<true, 4, 1><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        if (maxchi <= 16) tc::tc_gram_kernel<true, 1, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else if (maxchi <= 32) tc::tc_gram_kernel<true, 2, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<true, 4, 1><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
       }
       count_launch();
       stats_.gram_launches += 1;
@@ -918,6 +949,7 @@ static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntask
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
+  SlowLog sl("cudaLaunchKernelEx(jacobi)");
   TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2));
 }
 
@@ -1142,7 +1174,17 @@ void Engine::bp_level(const std::vector<int>& seq, const std::vector<int>& all_i
     build(legs, -1, 0, u);
     for (int it : g.its) results.push_back({it, leaf[leg_pos(u, dedge(u, seq[2 * it + 1]) / 2)]});
   };
-  const size_t budget = scratch_budget();
+  size_t need_total = 0;
+  {
+    std::vector<std::pair<int, int>> dry;
+    for (auto& gr : groups) {
+      const size_t n0 = nodes.size();
+      plan_group(gr, dry);
+      need_total += (nodes.size() - n0) * (((size_t)site_elems(gr.u) * esz_ + 255) & ~size_t(255));
+    }
+    nodes.clear();
+  }
+  const size_t budget = scratch_budget(need_total);
   size_t pos = 0;
   while (pos < groups.size()) {
     // chunk by scratch: one buffer per product node
@@ -1273,6 +1315,7 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
   stats_.bp_ms += ms;
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  if (wall_depth_ == 1) release_slabs();  // outermost call, stream drained by the event wait above
   return rep;
 }
 
@@ -1343,7 +1386,9 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
   const double eps = c64() ? 1.1920928955078125e-07 : 2.220446049250313e-16;
   const double sqrt_cutoff = ao.sqrt_cutoff >= 0 ? ao.sqrt_cutoff : 10 * eps;  // simple_update.jl:32-33
   const bool normalize = ao.normalize_tensors != 0;
-  const size_t budget = agreed_budget();
+  size_t need_total = 0;
+  for (int g : gate_ids) need_total += 3 * ((size_t)site_elems(verts[2 * g]) + (size_t)site_elems(verts[2 * g + 1])) * esz_;
+  const size_t budget = agreed_budget(need_total);
   size_t gpos = 0;
   while (gpos < gate_ids.size()) {
     size_t gend = gpos, bytes = 0;
@@ -1355,6 +1400,15 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       ++gend;
     }
     const int ng = (int)(gend - gpos);
+    // TNQS_SLOWLOG=1: host time of every phase of a batch that took longer than 60 ms in total
+    std::vector<std::pair<const char*, double>> phase_log;
+    auto phase_t0 = std::chrono::steady_clock::now();
+    auto phase_mark = [&](const char* name) {
+      if (!SlowLog::on()) return;
+      const auto now = std::chrono::steady_clock::now();
+      phase_log.push_back({name, std::chrono::duration<double, std::milli>(now - phase_t0).count()});
+      phase_t0 = now;
+    };
 
     // ---- 1. environments: eigendecompose every non-default incoming message --------------------
     struct EnvRef { int gate, site, pos, de, task; };
@@ -1406,6 +1460,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       TNQS_CUDA(cudaGetLastError());
     }
 
+    phase_mark("msg");
     // ---- 2. gauge: T̃ = T ×_ext √M (simple_update.jl:43-44) -------------------------------------
     std::vector<Chain> gauge(2 * ng);
     for (int k = 0; k < ng; ++k)
@@ -1413,6 +1468,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
     for (auto& en : envs) gauge[2 * en.gate + en.site].steps.push_back({en.pos, mt[en.task].sqrtM});
     run_chains(gauge);
 
+    phase_mark("gauge");
     // ---- 3. Gram of the gauged tensor over its external legs (R†R of the QR at :47-48) ---------
     std::vector<GramTask> gt(2 * ng);
     std::vector<double2*> G(2 * ng);
@@ -1447,6 +1503,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       exchange(bc);
     }
 
+    phase_mark("gram");
     // ---- 4. eig(G), θ, SVD(θ), truncation ------------------------------------------------------
     // Multi-GPU: the O(χ³) factorisations of gate k run on rank k mod R only (its "solver"); the kept
     // rank, truncation error, singular values and the two new factors then reach every rank with two
@@ -1632,6 +1689,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
                   "ncclAllGather(records)");
         stats_.kernel_launches += 1;
       }
+    phase_mark("factor-enqueue");
       // the host needs the kept ranks to size the new tensors: the one sync of the batch
       std::vector<int> keep(ng), flags(2 * std::max<size_t>(1, mt.size()));
       std::vector<double> err(ng);
@@ -1668,6 +1726,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         stats_.kernel_launches += 1;
       }
 
+    phase_mark("sync+factors");
       // ---- 5. un-gauge with the projector and contract with the new factor (:62-64) -----------
       std::vector<Chain> proj(2 * ng);
       for (int k = 0; k < ng; ++k)
@@ -1702,6 +1761,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         }
       }
       launch_mode(fin);
+    phase_mark("proj+final");
       // ---- 6. commit: tensors, bond dimension, messages (apply_gates.jl:126-140) ----------------
       std::vector<int> touched;
       std::vector<DiagTask> dt;
@@ -1741,6 +1801,16 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
     }
     stats_.two_site_gates += ng;
     free_temps();
+    phase_mark("commit");
+    if (SlowLog::on()) {
+      double tot = 0;
+      for (auto& ph : phase_log) tot += ph.second;
+      if (tot > 60.0) {
+        std::fprintf(stderr, "[tnqs slow] two-site batch of %d gates: host", ng);
+        for (auto& ph : phase_log) std::fprintf(stderr, " %s %.1f", ph.first, ph.second);
+        std::fprintf(stderr, " ms\n");
+      }
+    }
     gpos = gend;
   }
 }
@@ -1859,6 +1929,7 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
   stats_.su_ms += ms - (stats_.bp_ms - bp_before);
   cudaEventDestroy(t0);
   cudaEventDestroy(t1);
+  release_slabs();  // stream drained by the event wait above
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1903,6 +1974,7 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
   TNQS_CUDA(cudaMemcpyAsync(rho.data(), d_rho, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
   free_temps();
+  release_slabs();
   size_t opoff = 0;
   for (int i = 0; i < nobs; ++i) {
     const int d = phys_[verts[i]];
@@ -1971,6 +2043,7 @@ void Engine::expect_two_site(int nobs, const int32_t* verts, const double* ops, 
   TNQS_CUDA(cudaMemcpyAsync(E.data(), d_e, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
   free_temps();
+  release_slabs();
   size_t opoff = 0;
   for (int i = 0; i < nobs; ++i) {
     const int a = verts[2 * i], b = verts[2 * i + 1];

@@ -133,12 +133,13 @@ class Engine {
   struct Bcast { void* ptr; size_t bytes; int root; };
   void exchange(const std::vector<Bcast>& items);       // grouped broadcasts on the engine stream
   void allreduce_sum(double* dptr, size_t count);
-  size_t agreed_budget();
+  size_t agreed_budget(size_t need);
 
   // ---- helpers -------------------------------------------------------------------------------
   void* dalloc(size_t bytes);
   void* talloc(size_t bytes);  // temporary, freed by free_temps()
   void dfree(void* p);
+  void release_slabs();
   void free_temps();
   template <class T> T* upload(const std::vector<T>& v);
   int dedge(int src, int dst) const;
@@ -147,7 +148,7 @@ class Engine {
   void leg_view(int v, int pos, unsigned* outer, int* chi, unsigned* inner) const;
   void materialize_message(int de);
   void check_shapes() const;
-  size_t scratch_budget() const;
+  size_t scratch_budget(size_t need) const;
   bool c64() const { return dtype_ == TNQS_C64; }
 
   void launch_mode(std::vector<ModeTask>& tasks);

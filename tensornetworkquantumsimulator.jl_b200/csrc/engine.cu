@@ -386,7 +386,7 @@ size_t Engine::scratch_budget(size_t need) const {
   {
     size_t have = SlabPool::get().free_bytes(device_);
     for (auto& sl : slabs_) have += sl.second;
-    if (need > 0 && need + need / 8 + (64ull << 20) <= have) return have;
+    if (need > 0 && need + need / 32 + (32ull << 20) <= have) return have;  // ≤ 1/60 of a slab is lost to packing
   }
   size_t fr = 0, tot = 0;
   { SlowLog sl("cudaMemGetInfo"); cudaMemGetInfo(&fr, &tot); }
@@ -797,12 +797,12 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       int maxchi = 0;
       for (auto& t : tt[g]) maxchi = std::max(maxchi, t.chi);
       if (g == 0) {
-        if (maxchi <= 32) tc::tc_gram_kernel<false, 1, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else tc::tc_gram_kernel<false, 2, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
+        if (maxchi <= 32) tc::tc_gram_kernel<false, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<false, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
       } else {
-        if (maxchi <= 16) tc::tc_gram_kernel<true, 1, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else if (maxchi <= 32) tc::tc_gram_kernel<true, 2, 2><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
-        else tc::tc_gram_kernel<true, 4, 1><<<ncta, tc::TG_THREADS, smem_max[g], stream_>>>(dt, dc);
+        if (maxchi <= 16) tc::tc_gram_kernel<true, 1, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else if (maxchi <= 32) tc::tc_gram_kernel<true, 2, 2><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
+        else tc::tc_gram_kernel<true, 4, 1><<<ncta, tc::TC_THREADS, smem_max[g], stream_>>>(dt, dc);
       }
       count_launch();
       stats_.gram_launches += 1;

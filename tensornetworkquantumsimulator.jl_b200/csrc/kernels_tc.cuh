@@ -422,24 +422,11 @@ struct TcGramTask {
 
 // NIT = (X,Y) float4 pairs a thread stages per K step, PD = how many K steps ahead the global loads
 // run (register prefetch ring): the DRAM latency of step st+PD overlaps the split / MMA of step st.
-//
-// Warp-specialised: warps 0-7 are PRODUCERS (global → registers → hi/lo split → shared-memory stage), warp 8
-// lane 0 is the MMA ISSUER.  Two stages, two mbarrier rings: full[b] (8 arrivals, one per producer warp
-// after its stores + fence.proxy.async) and empty[b] (tcgen05.commit of the MMAs that read stage b).  The
-// producers never wait for the issuer to *issue*, only for stage b to be *consumed* two steps back, so the
-// split/store of step s+1 overlaps the MMA issue of step s.
-constexpr int TG_PRODUCERS = 256;
-constexpr int TG_THREADS = TG_PRODUCERS + 32;
-
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 template <bool LAST, int NIT, int PD>
-__global__ void __launch_bounds__(TG_THREADS) tc_gram_kernel(const TcGramTask* __restrict__ tasks, const int* __restrict__ cta_task) {
+__global__ void __launch_bounds__(TC_THREADS) tc_gram_kernel(const TcGramTask* __restrict__ tasks, const int* __restrict__ cta_task) {
   extern __shared__ __align__(1024) float smem[];
   __shared__ uint32_t s_tmem;
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_done;
+  __shared__ __align__(8) uint64_t s_bar[2];
   const TcGramTask t = tasks[cta_task[blockIdx.x]];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int split = blockIdx.x - t.cta_begin;
@@ -454,16 +441,12 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gram_kernel(const TcGramTask* _
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int b = 0; b < 2; ++b) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_full[b])), "r"(TG_PRODUCERS / 32));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_empty[b])), "r"(1));
-    }
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_done)), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&s_bar[1])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // zero both stages once: padded rows / columns must read as zeros
-  for (int i = tid; i < 2 * stage_floats; i += TG_THREADS) smem[i] = 0.f;
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  for (int i = tid; i < 2 * stage_floats; i += TC_THREADS) smem[i] = 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
@@ -477,142 +460,137 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gram_kernel(const TcGramTask* _
   const unsigned ce = t.CC;
   const int total_steps = (int)((t.CC + SCOLS - 1) / SCOLS);
   const int nstage = split < total_steps ? (total_steps - split + t.nsplit - 1) / t.nsplit : 0;
+  uint32_t ph[2] = {0, 0};
+  int used[2] = {0, 0};
+
+  // ---- per-thread constants of the staging pattern ----------------------------------------------------
+  // MID : item (row, q): row = (idx&7) + 8·(idx>>6), q = (idx>>3)&7 (row%8 fastest → conflict-free stores);
+  //       global element offset inside an outer slice: row·inner + 2q
+  // LAST: item (kl, l): column kl of the stage, float4 l of its 2χ-float row
+  int it_row[NIT], it_q[NIT];       // MID: row, q        LAST: kl, l
+  int offA[NIT], offB[NIT];         // shared-memory float offsets
+  bool it_ok[NIT];
+  const int w4 = chi >> 1;
   const int sboA = (t.MMp >> 5) * 512, sboB = (t.NNp >> 5) * 512;
-
-  if (warp < TG_PRODUCERS / 32) {
-    // =========================== producers ===============================================================
-    // MID : item (row, q): row = (idx&7) + 8·(idx>>6), q = (idx>>3)&7 (row%8 fastest → conflict-free stores);
-    //       global element offset inside an outer slice: row·inner + 2q
-    // LAST: item (kl, l): column kl of the stage, float4 l of its 2χ-float row
-    int it_row[NIT], it_q[NIT];       // MID: row, q        LAST: kl, l
-    int offA[NIT], offB[NIT];         // shared-memory float offsets
-    bool it_ok[NIT];
-    const int w4 = chi >> 1;
 #pragma unroll
-    for (int j = 0; j < NIT; ++j) {
-      const int idx = tid + j * TG_PRODUCERS;
-      if (!LAST) {
-        const int row = (idx & 7) + 8 * (idx >> 6), q = (idx >> 3) & 7;
-        it_row[j] = row; it_q[j] = q; it_ok[j] = row < chi;
-        const int m0 = 2 * row;  // Ycat rows (j,0) and (j,1)
-        offA[j] = (m0 & 7) * 4 + q * 32 + (m0 >> 3) * 256;
-        offB[j] = (row & 7) * 4 + q * 32 + (row >> 3) * 256;
-      } else {
-        const int kl = idx / w4, l = idx - kl * w4;
-        it_row[j] = kl; it_q[j] = l; it_ok[j] = kl < SCOLS;
-        const int r = kl & 3, ak = kl >> 2, am = l >> 3, c = (l & 7) >> 1, half = l & 1;
-        const int inatom = r * 128 + ((c ^ r) * 32) + half * 16;
-        offA[j] = (am * 512 + ak * sboA + inatom) >> 2;
-        offB[j] = (am * 512 + ak * sboB + inatom) >> 2;
-      }
+  for (int j = 0; j < NIT; ++j) {
+    const int idx = tid + j * TC_THREADS;
+    if (!LAST) {
+      const int row = (idx & 7) + 8 * (idx >> 6), q = (idx >> 3) & 7;
+      it_row[j] = row; it_q[j] = q; it_ok[j] = row < chi;
+      const int m0 = 2 * row;  // Ycat rows (j,0) and (j,1)
+      offA[j] = (m0 & 7) * 4 + q * 32 + (m0 >> 3) * 256;
+      offB[j] = (row & 7) * 4 + q * 32 + (row >> 3) * 256;
+    } else {
+      const int kl = idx / w4, l = idx - kl * w4;
+      it_row[j] = kl; it_q[j] = l; it_ok[j] = kl < SCOLS;
+      const int r = kl & 3, ak = kl >> 2, am = l >> 3, c = (l & 7) >> 1, half = l & 1;
+      const int inatom = r * 128 + ((c ^ r) * 32) + half * 16;
+      offA[j] = (am * 512 + ak * sboA + inatom) >> 2;
+      offB[j] = (am * 512 + ak * sboB + inatom) >> 2;
     }
-
-    float4 rx[PD][NIT], ry[PD][NIT];
-    auto load_stage = [&](int st, float4 (&x)[NIT], float4 (&y)[NIT]) {
-      const unsigned k0 = ((unsigned)st * (unsigned)t.nsplit + (unsigned)split) * SCOLS;
-      if (!LAST) {
-        // 16 complex columns of one outer slice (inner % 16 == 0 and every step starts on a multiple of 16)
-        const unsigned o = k0 / t.inner, n0 = k0 - o * t.inner;
-        const int nvalid = (int)min((unsigned)SCOLS, ce - k0);  // multiple of 2 by construction
-        const long long base = (long long)o * chi * t.inner + n0;
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-          x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
-          if (it_ok[j] && 2 * it_q[j] < nvalid) {
-            const long long a = base + (long long)it_row[j] * t.inner + 2 * it_q[j];
-            y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
-            x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
-          }
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-          x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
-          const unsigned col = k0 + it_row[j];
-          if (it_ok[j] && col < ce) {
-            const long long a = (long long)col * chi + 2 * it_q[j];
-            y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
-            x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
-          }
-        }
-      }
-    };
-#pragma unroll
-    for (int p = 0; p < PD; ++p)
-      if (p < nstage) load_stage(p, rx[p], ry[p]);
-
-    for (int st0 = 0; st0 < nstage; st0 += PD) {
-#pragma unroll
-      for (int p = 0; p < PD; ++p) {
-        const int st = st0 + p;
-        if (st >= nstage) break;
-        const int bsel = st & 1;
-        float* sA = smem + bsel * stage_floats;
-        float* sAl = sA + a_floats;
-        float* sBh = sAl + a_floats;
-        float* sBl = sBh + b_floats;
-        // stage bsel is free once the MMAs of step st−2 have completed (use u = st>>1 waits completion u−1)
-        if (st >= 2) mbar_wait(smem_u32(&s_empty[bsel]), (uint32_t)(((st >> 1) - 1) & 1));
-#pragma unroll
-        for (int j = 0; j < NIT; ++j) {
-          if (!it_ok[j]) continue;
-          const float4 x = rx[p][j], y = ry[p][j];
-          float4 hi, lo;
-          if (!LAST) {
-            split4(y, hi, lo);
-            *reinterpret_cast<float4*>(sA + offA[j]) = hi;
-            *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
-            const float4 yr = make_float4(y.y, -y.x, y.w, -y.z);  // (Yi, −Yr)
-            split4(yr, hi, lo);
-            *reinterpret_cast<float4*>(sA + offA[j] + 4) = hi;  // row m0+1 (m0 even → same 8-row group)
-            *reinterpret_cast<float4*>(sAl + offA[j] + 4) = lo;
-            split4(x, hi, lo);
-            *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
-            *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
-          } else {
-            split4(x, hi, lo);  // A = X (conjugated side: rows (i,ri))
-            *reinterpret_cast<float4*>(sA + offA[j]) = hi;
-            *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
-            split4(y, hi, lo);
-            *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
-            *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
-          }
-        }
-        if (st + PD < nstage) load_stage(st + PD, rx[p], ry[p]);  // refill this ring slot
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_full[bsel]));
-      }
-    }
-  } else if (lane == 0) {
-    // =========================== MMA issuer ==============================================================
-    // descriptors differ from stage to stage and k-step to k-step only in the 14-bit start-address field
-    const uint64_t a_d0 = LAST ? make_desc(smem_u32(smem), 512, sboA, 1) : make_desc(smem_u32(smem), 128, 1024, 0);
-    const uint64_t b_d0 = LAST ? make_desc(smem_u32(smem + 2 * a_floats), 512, sboB, 1)
-                               : make_desc(smem_u32(smem + 2 * a_floats), 128, 1024, 0);
-    const uint32_t a_ks = LAST ? (uint32_t)(2 * sboA) >> 4 : 256u >> 4;   // start-address step per k-step (16-byte units)
-    const uint32_t b_ks = LAST ? (uint32_t)(2 * sboB) >> 4 : 256u >> 4;
-    const uint32_t a_lo = (uint32_t)(a_floats * 4) >> 4, b_lo = (uint32_t)(b_floats * 4) >> 4;  // hi → lo image
-    const uint32_t st_step = (uint32_t)(stage_floats * 4) >> 4;
-    for (int st = 0; st < nstage; ++st) {
-      const int bsel = st & 1;
-      mbar_wait(smem_u32(&s_full[bsel]), (uint32_t)((st >> 1) & 1));
-      asm volatile("tcgen05.fence::after_thread_sync;");
-      const uint64_t ab = a_d0 + (uint64_t)(bsel * st_step), bb = b_d0 + (uint64_t)(bsel * st_step);
-#pragma unroll
-      for (int term = 0; term < 3; ++term) {
-        const uint64_t ad = ab + (term == 2 ? a_lo : 0u), bd = bb + (term == 1 ? b_lo : 0u);
-#pragma unroll
-        for (int ks = 0; ks < KC / 8; ++ks)
-          mma_tf32(tmem, ad + (uint64_t)(ks * a_ks), bd + (uint64_t)(ks * b_ks), idesc, (st | term | ks) != 0);
-      }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_empty[bsel])) : "memory");
-    }
-    // commits complete in issue order: this one fires when every MMA of the CTA has finished
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_done)) : "memory");
   }
-  if (warp < 4) mbar_wait(smem_u32(&s_done), 0);
 
+  float4 rx[PD][NIT], ry[PD][NIT];
+  auto load_stage = [&](int st, float4 (&x)[NIT], float4 (&y)[NIT]) {
+    const unsigned k0 = ((unsigned)st * (unsigned)t.nsplit + (unsigned)split) * SCOLS;
+    if (!LAST) {
+      // 16 complex columns of one outer slice (inner % 16 == 0 and every step starts on a multiple of 16)
+      const unsigned o = k0 / t.inner, n0 = k0 - o * t.inner;
+      const int nvalid = (int)min((unsigned)SCOLS, ce - k0);  // multiple of 2 by construction
+      const long long base = (long long)o * chi * t.inner + n0;
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
+        if (it_ok[j] && 2 * it_q[j] < nvalid) {
+          const long long a = base + (long long)it_row[j] * t.inner + 2 * it_q[j];
+          y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        x[j] = make_float4(0.f, 0.f, 0.f, 0.f); y[j] = x[j];
+        const unsigned col = k0 + it_row[j];
+        if (it_ok[j] && col < ce) {
+          const long long a = (long long)col * chi + 2 * it_q[j];
+          y[j] = __ldg(reinterpret_cast<const float4*>(t.Y + a));
+          x[j] = __ldg(reinterpret_cast<const float4*>(t.X + a));
+        }
+      }
+    }
+  };
+#pragma unroll
+  for (int p = 0; p < PD; ++p)
+    if (p < nstage) load_stage(p, rx[p], ry[p]);
+
+  for (int st0 = 0; st0 < nstage; st0 += PD) {
+#pragma unroll
+    for (int p = 0; p < PD; ++p) {
+      const int st = st0 + p;
+      if (st >= nstage) break;
+      const int bsel = st & 1;
+      float* sA = smem + bsel * stage_floats;
+      float* sAl = sA + a_floats;
+      float* sBh = sAl + a_floats;
+      float* sBl = sBh + b_floats;
+      if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }  // MMAs that read this stage are done
+#pragma unroll
+      for (int j = 0; j < NIT; ++j) {
+        if (!it_ok[j]) continue;
+        const float4 x = rx[p][j], y = ry[p][j];
+        float4 hi, lo;
+        if (!LAST) {
+          split4(y, hi, lo);
+          *reinterpret_cast<float4*>(sA + offA[j]) = hi;
+          *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
+          const float4 yr = make_float4(y.y, -y.x, y.w, -y.z);  // (Yi, −Yr)
+          split4(yr, hi, lo);
+          *reinterpret_cast<float4*>(sA + offA[j] + 4) = hi;  // row m0+1 (m0 even → same 8-row group)
+          *reinterpret_cast<float4*>(sAl + offA[j] + 4) = lo;
+          split4(x, hi, lo);
+          *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
+          *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
+        } else {
+          split4(x, hi, lo);  // A = X (conjugated side: rows (i,ri))
+          *reinterpret_cast<float4*>(sA + offA[j]) = hi;
+          *reinterpret_cast<float4*>(sAl + offA[j]) = lo;
+          split4(y, hi, lo);
+          *reinterpret_cast<float4*>(sBh + offB[j]) = hi;
+          *reinterpret_cast<float4*>(sBl + offB[j]) = lo;
+        }
+      }
+      if (st + PD < nstage) load_stage(st + PD, rx[p], ry[p]);  // refill this ring slot
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;");
+#pragma unroll
+        for (int term = 0; term < 3; ++term) {
+          const uint32_t a_base = smem_u32(term == 2 ? sAl : sA);
+          const uint32_t b_base = smem_u32(term == 1 ? sBl : sBh);
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ++ks) {
+            uint64_t ad, bd;
+            if (!LAST) {
+              ad = make_desc(a_base + ks * 256, 128, 1024, 0);
+              bd = make_desc(b_base + ks * 256, 128, 1024, 0);
+            } else {
+              ad = make_desc(a_base + ks * 2 * sboA, 512, sboA, 1);
+              bd = make_desc(b_base + ks * 2 * sboB, 512, sboB, 1);
+            }
+            mma_tf32(tmem, ad, bd, idesc, (st | term | ks) != 0);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&s_bar[bsel])) : "memory");
+      }
+      used[bsel] = 1;
+    }
+  }
+  // drain: wait for the last commit of each stage buffer (commits complete in issue order)
+  for (int bsel = 0; bsel < 2; ++bsel)
+    if (used[bsel]) { mbar_wait(smem_u32(&s_bar[bsel]), ph[bsel]); ph[bsel] ^= 1; }
   asm volatile("tcgen05.fence::after_thread_sync;");
   // ---- epilogue (once per CTA): TMEM → partial sums -------------------------------------------------
   double2* __restrict__ P = t.partial + (long long)split * chi * chi;

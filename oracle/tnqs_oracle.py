@@ -384,6 +384,25 @@ def apply_gates(c: OracleCache, gates: Sequence[np.ndarray], gate_verts: Sequenc
     return c, errs, reports
 
 
+def truncate(c: OracleCache, edge_groups, edge_sequence, maxdim: int, cutoff=None,
+             normalize_tensors: bool = True, bp_update_kwargs: Optional[dict] = None) -> OracleCache:
+    """`truncate(bpc; maxdim, cutoff, edge_color=true)` (src/truncate.jl:12-30): per edge-colour group an
+    identity two-site gate on every truncatable edge (`truncatable_edge`, :5-10: bond dimension > 1)
+    through `apply_gate!`, then one BP `update`.  `edge_groups` = lists of (v1, v2) index pairs."""
+    if bp_update_kwargs is None:
+        bp_update_kwargs = default_bp_update_kwargs(c)
+    c = c.copy()
+    for grp in edge_groups:
+        for (a, b) in grp:
+            if c.T[a].shape[c.leg(a, b)] <= 1:
+                continue
+            d = c.T[a].shape[0] * c.T[b].shape[0]
+            apply_gate(c, np.eye(d, dtype=c.dtype), [a, b], maxdim=maxdim, cutoff=cutoff,
+                       normalize_tensors=normalize_tensors)
+        c, _ = bp_update(c, edge_sequence, **bp_update_kwargs)
+    return c
+
+
 # ---------------------------------------------------------------------------------------------
 # local expectation values (src/expect.jl:59-82, tensornetworkstate.jl:50-67)
 # ---------------------------------------------------------------------------------------------

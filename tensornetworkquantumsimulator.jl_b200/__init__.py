@@ -8,7 +8,7 @@ from .graphs import (NamedGraph, named_grid, named_path_graph, named_comb_tree, 
 from .gates import (ArgumentError, gate_matrix, observable_matrix, register_gate, register_alias,  # noqa: F401
                     unregister_gate)
 from .api import (TensorNetworkState, BeliefPropagationCache, tensornetworkstate, zerostate,  # noqa: F401
-                  random_tensornetworkstate, apply_gates, apply_circuit, update, expect, network,
+                  random_tensornetworkstate, apply_gates, apply_circuit, truncate, update, expect, network,
                   maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays)
 from ._lib import TnqsError, LIB_PATH  # noqa: F401
 from .distributed import partition_vertices, cut_edges, shard  # noqa: F401

@@ -181,6 +181,13 @@ class BeliefPropagationCache:
         b = self.bond_dims()
         return int(b.max()) if len(b) else 1
 
+    def site_shape(self, v) -> Tuple[int, ...]:
+        """Shape (d, χ_0, …) of the site tensor of `v` (no data transfer)."""
+        nd = C.c_int(64)
+        shp = (C.c_int64 * 64)()
+        _lib.check(self._lib.tnqs_site_shape(self._h, self.graph.index[v], C.byref(nd), shp))
+        return tuple(int(shp[k]) for k in range(nd.value))
+
     def site(self, v) -> np.ndarray:
         """`network(ψ_bpc)[v]`: download one site tensor."""
         i = self.graph.index[v]
@@ -393,6 +400,42 @@ def apply_gates(circuit: Sequence, psi, apply_kwargs: Optional[dict] = None,
 
 
 apply_circuit = apply_gates
+
+
+def truncate(bpc: BeliefPropagationCache, maxdim: int, cutoff=None, edge_color: bool = True,
+             normalize_tensors: bool = True, bp_update_kwargs: Optional[dict] = None,
+             edge_groups: Optional[Sequence] = None, inplace: bool = False) -> BeliefPropagationCache:
+    """`truncate(bpc; bp_update_kwargs, maxdim, cutoff, edge_color, normalize_tensors)` (`src/truncate.jl:12-38`):
+    an identity two-site gate through the simple update on every truncatable edge (bond dimension > 1), one
+    edge-colour group at a time with a BP `update` after each group (`edge_color=False`: after each edge).
+    No new device code: a colour group is one batched `tnqs_apply_gates` call with `update_cache = 0`.
+    `edge_groups` overrides the colouring (the reference's comes from an integer program and is not unique)."""
+    from .graphs import edge_color as _edge_color
+    out = bpc if inplace else bpc.copy()
+    g = out.graph
+    kw = bp_update_kwargs if bp_update_kwargs is not None else default_bp_update_kwargs(out)
+    akw = dict(maxdim=maxdim, normalize_tensors=normalize_tensors)
+    if cutoff is not None:
+        akw["cutoff"] = cutoff
+    if edge_groups is None:
+        if edge_color:
+            z = max(g.degree(v) for v in g.vertices())
+            edge_groups = _edge_color(g, z)
+        else:
+            edge_groups = [[e] for e in g.edges]
+    phys = {v: out.site_shape(v)[0] for v in g.vertices()}
+    for grp in edge_groups:
+        dims = out.bond_dims()
+        circ = []
+        for (a, b) in grp:
+            if dims[g.edge_id(a, b)] <= 1:  # truncatable_edge (truncate.jl:5-10)
+                continue
+            d = phys[a] * phys[b]
+            circ.append((np.eye(d, dtype=complex), [a, b]))
+        if circ:
+            out, _ = apply_gates(circ, out, apply_kwargs=akw, update_cache=False, inplace=True)
+        out = update(out, inplace=True, **kw)
+    return out
 
 
 def _collect_observable(obs, g: NamedGraph):

@@ -348,3 +348,31 @@ def test_other_lattices_match_oracle(name):
     zs = np.array(tq.expect(psi, [("Z", [v]) for v in probe]))
     zo = np.array([orc.expect_local(c, g.index[v], Z) for v in probe])
     assert np.max(np.abs(zs - zo)) < 1e-8
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_truncate_matches_oracle(dtype, tol):
+    """`truncate(bpc; maxdim)` (src/truncate.jl:12-30; reference test test_truncate.jl:29-33): identity gates
+    through the batched simple update per colour group + BP update, against the oracle with the same groups."""
+    g = tq.named_grid((3, 3))
+    layer = tfim_layer(g)
+    seq = tq.bipartite_edge_sequence(g)
+    bptol = 1e-13 if dtype == np.complex128 else 1e-10
+    bp = dict(maxiter=300, tolerance=bptol, edge_sequence=seq)
+    psi = tq.BeliefPropagationCache(tq.zerostate(dtype, g))
+    for _ in range(3):
+        psi, _ = tq.apply_gates(layer, psi, apply_kwargs=dict(maxdim=6, cutoff=1e-12), bp_update_kwargs=bp)
+    assert psi.maxvirtualdim() > 3
+    c = oracle_from_bpc(psi)
+    groups = tq.edge_color(g, 4)
+    out = tq.truncate(psi, maxdim=3, bp_update_kwargs=bp, edge_groups=groups)
+    assert psi.maxvirtualdim() > 3 and out.maxvirtualdim() <= 3  # functional copy, bound respected
+    ogroups = [[(g.index[a], g.index[b]) for a, b in grp] for grp in groups]
+    co = orc.truncate(c, ogroups, seq_idx(g, seq), maxdim=3, bp_update_kwargs=dict(maxiter=300, tolerance=1e-13))
+    assert list(out.bond_dims()) == co.bond_dims()
+    ftol = tol if dtype == np.complex128 else 10 * tol
+    zs = np.array(tq.expect(out, [("Z", [v]) for v in g.vertices()]))
+    zo = np.array([orc.expect_local(co, i, Z) for i in range(g.nv)])
+    assert np.max(np.abs(zs - zo)) < 100 * ftol
+    ov, n1, n2 = state_overlap(oracle_from_bpc(out), co)
+    assert abs(ov - 1) < 100 * ftol

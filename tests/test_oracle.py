@@ -226,3 +226,28 @@ def test_gate_conventions():
     tq.unregister_gate("MyZRot")
     with pytest.raises(tq.ArgumentError):
         tq.gate_matrix("MyZRot", 1, 0.3)
+
+
+def test_truncate_reduces_bond_dimension_and_keeps_fidelity():
+    """/root/reference/test/test_truncate.jl:29-33 flavour: after `truncate(bpc; maxdim)` every bond is
+    ≤ maxdim and the fidelity with the untruncated state is in [0, 1] (and close to 1 for a mild cut)."""
+    import tnqs_b200 as tq
+    from helpers_cpu import tfim_layer_cpu
+    g = tq.named_grid((3, 2))
+    layer, gm, gv = tfim_layer_cpu(g)
+    seq = [(g.index[a], g.index[b]) for a, b in tq.bipartite_edge_sequence(g)]
+    c = orc.product_state(g.nv, g.edge_uv(), [(1.0, 0.0)] * g.nv, np.complex128)
+    for _ in range(3):
+        c, _, _ = orc.apply_gates(c, gm, gv, seq, dict(maxdim=8, cutoff=1e-14), dict(maxiter=100, tolerance=1e-12))
+    assert c.maxvirtualdim() > 2
+    groups = [[(g.index[a], g.index[b]) for a, b in grp] for grp in tq.edge_color(g, 3)]
+    t = orc.truncate(c, groups, seq, maxdim=2, bp_update_kwargs=dict(maxiter=100, tolerance=1e-12))
+    assert t.maxvirtualdim() <= 2
+    p1, p2 = orc.to_statevector(c), orc.to_statevector(t)
+    f = abs(np.vdot(p1, p2)) ** 2 / (np.vdot(p1, p1).real * np.vdot(p2, p2).real)
+    assert 0.0 <= f <= 1.0 + 1e-12
+    assert f > 0.9
+    same = orc.truncate(c, groups, seq, maxdim=64, bp_update_kwargs=dict(maxiter=100, tolerance=1e-12))
+    p3 = orc.to_statevector(same)
+    f3 = abs(np.vdot(p1, p3)) ** 2 / (np.vdot(p1, p1).real * np.vdot(p3, p3).real)
+    assert abs(f3 - 1) < 1e-10  # nothing to cut: an identity gate through the simple update changes nothing

@@ -133,6 +133,14 @@ int  tnqs_expect_local(tnqs_handle h, int nobs, const int32_t* verts, const doub
 int  tnqs_expect_two_site(tnqs_handle h, int nobs, const int32_t* verts /*2*nobs*/,
                           const double* op_mats /*2 d×d per obs*/, double* out /*2*nobs*/);
 
+/* vertex_scalar(bpc, v) (abstractbeliefpropagationcache.jl:22-28): the contraction of T_v, conj(T_v) and the
+ * messages into v — the numerator terms of partitionfunction / freenergy (:289-303); out is complex128 per
+ * vertex.  edge_scalar (beliefpropagationcache.jl:47-49) only needs the two χ×χ messages: host side. */
+int  tnqs_vertex_scalars(tnqs_handle h, int n, const int32_t* verts, double* out /*2*n*/);
+/* tn[v] <- factor_v * tn[v] in place (rescale_vertices!, beliefpropagationcache.jl:82-101);
+ * factors are complex128, each vertex at most once. */
+int  tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* factors /*2*n*/);
+
 /* --- multi-GPU: vertex ownership + NCCL exchange --------------------------- */
 
 /* Join an NCCL communicator: every rank holds the full graph, owns the site tensors of the

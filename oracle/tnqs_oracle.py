@@ -425,6 +425,54 @@ def expect_local(c: OracleCache, v: int, op: np.ndarray, coeff=1.0):
     return coeff * np.sum(np.asarray(op) * rho.T) / np.trace(rho)
 
 
+# ---------------------------------------------------------------------------------------------
+# scalars of the BP fixed point, rescaling, norm
+# ---------------------------------------------------------------------------------------------
+def vertex_scalar(c: OracleCache, v: int):
+    """`vertex_scalar` (src/MessagePassing/abstractbeliefpropagationcache.jl:22-28)."""
+    return np.trace(rdm_local(c, v).astype(_wide(c.dtype)))
+
+
+def edge_scalar(c: OracleCache, u: int, v: int):
+    """`edge_scalar` (src/MessagePassing/beliefpropagationcache.jl:47-49): message(e)·message(reverse(e))."""
+    return np.sum(c.message(u, v).astype(_wide(c.dtype)) * c.message(v, u).astype(_wide(c.dtype)))
+
+
+def freenergy(c: OracleCache):
+    """`freenergy` (abstractbeliefpropagationcache.jl:289-300): Σ log(vertex scalars) − Σ log(edge scalars)."""
+    num = np.array([vertex_scalar(c, v) for v in range(c.nv)], dtype=complex)
+    den = np.array([edge_scalar(c, u, v) for (u, v) in c.edges], dtype=complex)
+    if np.any(den == 0):
+        return -np.inf
+    return np.sum(np.log(num)) - np.sum(np.log(den))
+
+
+def partitionfunction(c: OracleCache):
+    """`partitionfunction` (:302-304); for a TensorNetworkState cache this is `norm_sqr(alg="bp")` (norm_sqr.jl:72-78)."""
+    return np.exp(freenergy(c))
+
+
+def rescale(c: OracleCache) -> OracleCache:
+    """`rescale` = `rescale_messages!` (beliefpropagationcache.jl:127-140) then `rescale_vertices!` (:82-101)."""
+    c = c.copy()
+    for (u, v) in c.edges:
+        me, mer = c.message(u, v), c.message(v, u)
+        me = me / np.linalg.norm(me)
+        mer = mer / np.linalg.norm(mer)
+        n = np.sum(me.astype(_wide(c.dtype)) * mer.astype(_wide(c.dtype)))
+        if np.imag(n) == 0:
+            sg = np.sign(np.real(n))
+            me = me * sg
+            n = n * sg
+        c.msg[(u, v)] = (me / np.sqrt(n)).astype(c.dtype)
+        c.msg[(v, u)] = (mer / np.sqrt(n)).astype(c.dtype)
+    for v in range(c.nv):
+        vn = vertex_scalar(c, v)
+        sg = np.sign(np.real(vn)) if np.imag(vn) == 0 else 1.0
+        c.T[v] = (c.T[v] * (sg / np.sqrt(vn))).astype(c.dtype)
+    return c
+
+
 def expect_two_site(c: OracleCache, v1: int, v2: int, op1: np.ndarray, op2: np.ndarray, coeff=1.0):
     """Adjacent two-site observable: region {v1,v2} is its own Steiner tree (expect.jl:67)."""
     if coeff == 0:

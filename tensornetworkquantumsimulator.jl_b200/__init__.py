@@ -9,6 +9,8 @@ from .gates import (ArgumentError, gate_matrix, observable_matrix, register_gate
                     unregister_gate)
 from .api import (TensorNetworkState, BeliefPropagationCache, tensornetworkstate, zerostate,  # noqa: F401
                   random_tensornetworkstate, apply_gates, apply_circuit, truncate, update, expect, network,
-                  maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays)
+                  maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays,
+                  vertex_scalar, vertex_scalars, edge_scalar, edge_scalars, scalar_factors_quotient, freenergy,
+                  partitionfunction, rescale_messages, rescale_vertices, rescale, norm_sqr, normalize)
 from ._lib import TnqsError, LIB_PATH  # noqa: F401
 from .distributed import partition_vertices, cut_edges, shard  # noqa: F401

@@ -438,6 +438,112 @@ def truncate(bpc: BeliefPropagationCache, maxdim: int, cutoff=None, edge_color: 
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# scalars of the BP fixed point, rescaling, norm
+# ---------------------------------------------------------------------------------------------
+def vertex_scalars(bpc: BeliefPropagationCache, vertices: Optional[Sequence] = None) -> np.ndarray:
+    """`vertex_scalars(bpc, vertices)` (`abstractbeliefpropagationcache.jl:22-28,134-138`): ⟨T_v|msgs|T_v⟩."""
+    vs = list(bpc.graph.vertices()) if vertices is None else list(vertices)
+    idx, idx_p = _i32(np.array([bpc.graph.index[v] for v in vs], dtype=np.int32))
+    out = np.zeros(2 * len(vs), dtype=np.float64)
+    _lib.check(bpc._lib.tnqs_vertex_scalars(bpc._h, len(vs), idx_p, out.ctypes.data_as(C.POINTER(C.c_double))))
+    return out.view(np.complex128).copy()
+
+
+def vertex_scalar(bpc: BeliefPropagationCache, v):
+    return vertex_scalars(bpc, [v])[0]
+
+
+def edge_scalar(bpc: BeliefPropagationCache, edge):
+    """`edge_scalar(bpc, e)` (`beliefpropagationcache.jl:47-49`): scalar(message(e) * message(reverse(e)))."""
+    a, b = edge
+    return np.sum(bpc.message((a, b)).astype(np.complex128) * bpc.message((b, a)).astype(np.complex128))
+
+
+def edge_scalars(bpc: BeliefPropagationCache, edges: Optional[Sequence] = None) -> np.ndarray:
+    es = list(bpc.graph.edges) if edges is None else list(edges)
+    return np.array([edge_scalar(bpc, e) for e in es], dtype=np.complex128)
+
+
+def scalar_factors_quotient(bpc: BeliefPropagationCache):
+    """`scalar_factors_quotient` (`abstractbeliefpropagationcache.jl:146-148`)."""
+    return vertex_scalars(bpc), edge_scalars(bpc)
+
+
+def freenergy(bpc: BeliefPropagationCache):
+    """`freenergy` (`abstractbeliefpropagationcache.jl:289-300`)."""
+    num, den = scalar_factors_quotient(bpc)
+    if np.any(den == 0):
+        return -np.inf
+    return np.sum(np.log(num)) - np.sum(np.log(den))
+
+
+def partitionfunction(bpc: BeliefPropagationCache):
+    """`partitionfunction` (`abstractbeliefpropagationcache.jl:302-304`)."""
+    return np.exp(freenergy(bpc))
+
+
+def rescale_messages(bpc: BeliefPropagationCache, edges: Optional[Sequence] = None, inplace: bool = False):
+    """`rescale_messages!` (`beliefpropagationcache.jl:127-140`): both messages of an edge normalised, then divided
+    by the square root of their contraction so that `edge_scalar == 1`."""
+    out = bpc if inplace else bpc.copy()
+    for (a, b) in (list(out.graph.edges) if edges is None else list(edges)):
+        me, mer = out.message((a, b)).astype(np.complex128), out.message((b, a)).astype(np.complex128)
+        me /= np.linalg.norm(me)
+        mer /= np.linalg.norm(mer)
+        n = np.sum(me * mer)
+        if n.imag == 0:
+            sg = np.sign(n.real)
+            me *= sg
+            n *= sg
+        out.setmessage((a, b), me / np.sqrt(n))
+        out.setmessage((b, a), mer / np.sqrt(n))
+    return out
+
+
+def rescale_vertices(bpc: BeliefPropagationCache, vertices: Optional[Sequence] = None, inplace: bool = False):
+    """`rescale_vertices!` (`beliefpropagationcache.jl:82-101`) for a TensorNetworkState: tn[v] *= s/√vertex_scalar."""
+    out = bpc if inplace else bpc.copy()
+    vs = list(out.graph.vertices()) if vertices is None else list(vertices)
+    vn = vertex_scalars(out, vs)
+    sg = np.where(vn.imag == 0, np.sign(vn.real), 1.0)
+    f = np.ascontiguousarray(sg / np.sqrt(vn), dtype=np.complex128)
+    idx, idx_p = _i32(np.array([out.graph.index[v] for v in vs], dtype=np.int32))
+    _lib.check(out._lib.tnqs_scale_sites(out._h, len(vs), idx_p, f.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))))
+    return out
+
+
+def rescale(bpc: BeliefPropagationCache, inplace: bool = False) -> BeliefPropagationCache:
+    """`rescale` / `rescale!` (`abstractbeliefpropagationcache.jl:318-328`)."""
+    out = bpc if inplace else bpc.copy()
+    rescale_messages(out, inplace=True)
+    rescale_vertices(out, inplace=True)
+    return out
+
+
+def norm_sqr(psi, alg: str = "bp", cache_update_kwargs: Optional[dict] = None, device: int = 0):
+    """`norm_sqr(ψ | ψ_bpc; alg="bp")` (`src/norm_sqr.jl:72-84`): the BP partition function of ⟨ψ|ψ⟩."""
+    if alg != "bp":
+        raise ArgumentError('norm_sqr: only alg="bp" is implemented on the device path')
+    if isinstance(psi, TensorNetworkState):
+        bpc = BeliefPropagationCache(psi, device=device)
+        kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(bpc)
+        psi = update(bpc, inplace=True, **kw)
+    return partitionfunction(psi)
+
+
+def normalize(tns: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Optional[dict] = None,
+              device: int = 0) -> TensorNetworkState:
+    """`normalize(tns; alg="bp")` (`src/normalize.jl:1-6`): update, rescale!, network."""
+    if alg != "bp":
+        raise ArgumentError('normalize: only alg="bp" is implemented')
+    bpc = BeliefPropagationCache(tns, device=device)
+    kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(bpc)
+    bpc = update(bpc, inplace=True, **kw)
+    rescale(bpc, inplace=True)
+    return bpc.network()
+
+
 def _collect_observable(obs, g: NamedGraph):
     """`collectobservable` (`expect.jl:159-175`)."""
     coeff = 1 if len(obs) == 2 else obs[-1]

@@ -131,6 +131,18 @@ int tnqs_expect_local(tnqs_handle h, int nobs, const int32_t* verts, const doubl
     E(h).expect_local(nobs, verts, op_mats, out);
   });
 }
+int tnqs_vertex_scalars(tnqs_handle h, int n, const int32_t* verts, double* out) {
+  return guarded([&] {
+    if (n > 0 && (!verts || !out)) throw Error(TNQS_EINVAL, "null argument");
+    E(h).vertex_scalars(n, verts, out);
+  });
+}
+int tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* factors) {
+  return guarded([&] {
+    if (n > 0 && (!verts || !factors)) throw Error(TNQS_EINVAL, "null argument");
+    E(h).scale_sites(n, verts, factors);
+  });
+}
 int tnqs_expect_two_site(tnqs_handle h, int nobs, const int32_t* verts, const double* op_mats, double* out) {
   return guarded([&] {
     if (nobs > 0 && (!verts || !op_mats || !out)) throw Error(TNQS_EINVAL, "null argument");

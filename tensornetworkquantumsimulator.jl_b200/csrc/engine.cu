@@ -1935,14 +1935,15 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
 // ------------------------------------------------------------------------------------------------
 // expectation values (expect.jl:59-82)
 // ------------------------------------------------------------------------------------------------
-void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, double* out) {
+// un-normalised single-site density matrices ρ_v[s][s'] = ⟨T_v| msgs |T_v⟩ with the physical legs open
+// (the common part of expect.jl:59-82 and vertex_scalar, abstractbeliefpropagationcache.jl:22-28)
+void Engine::local_rdms(int n, const int32_t* verts, std::vector<cplx>& rho, std::vector<size_t>& offs) {
   TNQS_CUDA(cudaSetDevice(device_));
   check_shapes();
-  if (nobs <= 0) return;
-  std::vector<Chain> chains(nobs);
-  for (int i = 0; i < nobs; ++i) {
+  std::vector<Chain> chains(n);
+  for (int i = 0; i < n; ++i) {
     const int v = verts[i];
-    if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "observable vertex out of range");
+    if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
     chains[i].v = v;
     for (size_t p = 0; p < inc_[v].size(); ++p) {
       const int de = dedge(inc_[v][p].nbr, v);
@@ -1951,17 +1952,16 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
     }
   }
   run_chains(chains);
-  std::vector<GramTask> gt(nobs);
-  std::vector<double2*> outs(nobs);
+  std::vector<double2*> outs(n);
   size_t tot = 0;
-  std::vector<size_t> offs(nobs);
-  for (int i = 0; i < nobs; ++i) { offs[i] = tot; tot += (size_t)phys_[verts[i]] * phys_[verts[i]]; }
+  offs.assign(n, 0);
+  for (int i = 0; i < n; ++i) { offs[i] = tot; tot += (size_t)phys_[verts[i]] * phys_[verts[i]]; }
   double2* d_rho = (double2*)talloc(tot * sizeof(double2));
   TNQS_CUDA(cudaMemsetAsync(d_rho, 0, tot * sizeof(double2), stream_));
   {
     std::vector<GramTask> gto;
     std::vector<double2*> oo;
-    for (int i = 0; i < nobs; ++i) {
+    for (int i = 0; i < n; ++i) {
       outs[i] = d_rho + offs[i];
       if (!owns(verts[i])) continue;  // the owner contracts; the others contribute zeros to the sum
       gto.push_back(gram_task(verts[i], -1, 1, site_[verts[i]], chains[i].result));
@@ -1970,11 +1970,18 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
     launch_gram(gto, true, oo, /*transpose=*/true);  // buffer[s*d+s'] = ρ[s][s']
     allreduce_sum(reinterpret_cast<double*>(d_rho), 2 * tot);
   }
-  std::vector<cplx> rho(tot);
+  rho.assign(tot, cplx(0, 0));
   TNQS_CUDA(cudaMemcpyAsync(rho.data(), d_rho, tot * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
   free_temps();
   release_slabs();
+}
+
+void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, double* out) {
+  if (nobs <= 0) return;
+  std::vector<cplx> rho;
+  std::vector<size_t> offs;
+  local_rdms(nobs, verts, rho, offs);
   size_t opoff = 0;
   for (int i = 0; i < nobs; ++i) {
     const int d = phys_[verts[i]];
@@ -1991,6 +1998,41 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
     const cplx val = num / den;
     out[2 * i] = val.real(); out[2 * i + 1] = val.imag();
   }
+}
+
+// vertex_scalar(bpc, v) (abstractbeliefpropagationcache.jl:22-28): ⟨T_v| incoming messages |T_v⟩ = tr ρ_v
+void Engine::vertex_scalars(int n, const int32_t* verts, double* out) {
+  if (n <= 0) return;
+  std::vector<cplx> rho;
+  std::vector<size_t> offs;
+  local_rdms(n, verts, rho, offs);
+  for (int i = 0; i < n; ++i) {
+    const int d = phys_[verts[i]];
+    cplx tr = 0;
+    for (int s = 0; s < d; ++s) tr += rho[offs[i] + (size_t)s * d + s];
+    out[2 * i] = tr.real(); out[2 * i + 1] = tr.imag();
+  }
+}
+
+// tn[v] ← f_v · tn[v] (rescale_vertices!, beliefpropagationcache.jl:82-101): the one-site kernel with U = f·1
+void Engine::scale_sites(int n, const int32_t* verts, const double* factors) {
+  if (n <= 0) return;
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  std::vector<std::pair<int, std::vector<cplx>>> g;
+  std::vector<char> seen(nv_, 0);
+  for (int i = 0; i < n; ++i) {
+    const int v = verts[i];
+    if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+    if (seen[v]) throw Error(TNQS_EINVAL, "tnqs_scale_sites: a vertex may appear only once");
+    seen[v] = 1;
+    const int d = phys_[v];
+    std::vector<cplx> U((size_t)d * d, cplx(0, 0));
+    for (int s = 0; s < d; ++s) U[(size_t)s * d + s] = cplx(factors[2 * i], factors[2 * i + 1]);
+    g.push_back({v, U});
+  }
+  apply_one_site_batch(g, /*normalize=*/false);
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
 void Engine::expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out) {

@@ -75,6 +75,8 @@ class Engine {
   tnqs_bp_report bp_update(const tnqs_bp_opts* opts);
   void expect_local(int nobs, const int32_t* verts, const double* ops, double* out);
   void expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out);
+  void vertex_scalars(int n, const int32_t* verts, double* out);
+  void scale_sites(int n, const int32_t* verts, const double* factors);
 
   // multi-GPU: vertex ownership + NCCL exchange of the replicated small data (messages, Gram matrices)
   void comm_init(int rank, int nranks, const void* unique_id128, const int32_t* owner);
@@ -160,6 +162,7 @@ class Engine {
   ModeTask mode_task(int v, int pos, const void* in, void* out, const void* mat) const;
   GramTask gram_task(int v, int pos, int planes, const void* X, const void* Y) const;
 
+  void local_rdms(int n, const int32_t* verts, std::vector<std::complex<double>>& rho, std::vector<size_t>& offs);
   void normalize_sites(const std::vector<int>& vs);
   void apply_one_site_batch(const std::vector<std::pair<int, std::vector<std::complex<double>>>>& g,
                             bool normalize);

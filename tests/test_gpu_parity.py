@@ -376,3 +376,42 @@ def test_truncate_matches_oracle(dtype, tol):
     assert np.max(np.abs(zs - zo)) < 100 * ftol
     ov, n1, n2 = state_overlap(oracle_from_bpc(out), co)
     assert abs(ov - 1) < 100 * ftol
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_partitionfunction_rescale_normalize(dtype, tol):
+    """vertex/edge scalars, freenergy / partitionfunction (abstractbeliefpropagationcache.jl:22-28,289-304,
+    beliefpropagationcache.jl:47-49), rescale (:82-101,127-140) and normalize(alg="bp") (normalize.jl:1-6)
+    against the oracle on a loopy graph, and the exactness on a tree of test_beliefpropagation.jl:24-29."""
+    ftol = tol if dtype == np.complex128 else 10 * tol
+    g = tq.named_grid((3, 3))
+    dims = [2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=31)
+    seq = tq.bipartite_edge_sequence(g)
+    bpc = tq.update(tq.BeliefPropagationCache(psi), maxiter=200, tolerance=1e-13 if dtype == np.complex128 else 1e-9,
+                    edge_sequence=seq)
+    c = oracle_from_bpc(bpc)
+    vs = tq.vertex_scalars(bpc)
+    vo = np.array([orc.vertex_scalar(c, i) for i in range(g.nv)])
+    assert rel(vs, vo) < 100 * ftol
+    es = tq.edge_scalars(bpc)
+    eo = np.array([orc.edge_scalar(c, u, v) for (u, v) in c.edges])
+    assert rel(es, eo) < 100 * ftol
+    z, zo = tq.partitionfunction(bpc), orc.partitionfunction(c)
+    assert abs(z - zo) < 100 * ftol * abs(zo)
+    assert abs(tq.norm_sqr(bpc, alg="bp") - z) < 1e-12 * abs(z)
+    r = tq.rescale(bpc)
+    assert abs(tq.partitionfunction(bpc) - z) < 1e-12 * abs(z)  # functional copy: the input is untouched
+    assert np.max(np.abs(tq.vertex_scalars(r) - 1)) < 100 * ftol
+    assert np.max(np.abs(tq.edge_scalars(r) - 1)) < 100 * ftol
+    ro = orc.rescale(c)
+    for i, v in enumerate(g.vertices()):
+        assert rel(r.site(v), ro.T[i]) < 100 * ftol
+    # tree: BP is exact, so normalize(alg="bp") returns a state of unit norm
+    gt = tq.named_comb_tree((3, 2))
+    pt = ragged_state(gt, [2, 3, 2, 3, 2][:gt.ne], dtype, seed=32)
+    nt = tq.normalize(pt, alg="bp")
+    full = orc.to_statevector(oracle_from_tns(nt))
+    assert abs(np.vdot(full, full) - 1) < 100 * ftol
+    full0 = orc.to_statevector(oracle_from_tns(pt))
+    assert abs(tq.norm_sqr(pt, alg="bp") - np.vdot(full0, full0)) < 100 * ftol * abs(np.vdot(full0, full0))

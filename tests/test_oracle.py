@@ -251,3 +251,21 @@ def test_truncate_reduces_bond_dimension_and_keeps_fidelity():
     p3 = orc.to_statevector(same)
     f3 = abs(np.vdot(p1, p3)) ** 2 / (np.vdot(p1, p1).real * np.vdot(p3, p3).real)
     assert abs(f3 - 1) < 1e-10  # nothing to cut: an identity gate through the simple update changes nothing
+
+
+def test_partitionfunction_exact_on_tree_and_rescale():
+    """/root/reference/test/test_beliefpropagation.jl:24-29 (Z_bp = exact on a tree) and the rescale! contract
+    (abstractbeliefpropagationcache.jl:318-322: afterwards every vertex and edge scalar is 1)."""
+    g = tq.named_comb_tree((3, 2))
+    c = orc.random_state(g.nv, g.edge_uv(), 2, 3, np.complex128, seed=5)
+    seq = [(g.index[a], g.index[b]) for a, b in tq.forest_cover_edge_sequence(g)]
+    c, _ = orc.bp_update(c, seq, maxiter=1, tolerance=None)
+    psi = orc.to_statevector(c)
+    z = orc.partitionfunction(c)
+    assert abs(z - np.vdot(psi, psi)) < 1e-10 * abs(z)
+    r = orc.rescale(c)
+    assert np.allclose([orc.vertex_scalar(r, v) for v in range(r.nv)], 1.0, atol=1e-12)
+    assert np.allclose([orc.edge_scalar(r, u, v) for (u, v) in r.edges], 1.0, atol=1e-12)
+    assert abs(orc.partitionfunction(r) - 1) < 1e-12
+    p2 = orc.to_statevector(r)
+    assert abs(np.vdot(p2, p2) - 1) < 1e-10  # exact on a tree: the rescaled state is normalised

@@ -473,6 +473,29 @@ def rescale(c: OracleCache) -> OracleCache:
     return c
 
 
+def renyi_entropy_matrix(rho: np.ndarray, alpha: float, normalize: bool = True) -> float:
+    """`renyi_entropy(ρ::AbstractMatrix, α)` (src/entanglement.jl:21-29)."""
+    rho = np.asarray(rho)
+    if normalize:
+        rho = rho / np.trace(rho)
+    lam = np.linalg.eigvalsh(rho)
+    eps = np.finfo(lam.dtype).eps
+    lam = lam[np.abs(lam) > 10 * eps]
+    if alpha == 1:
+        return float(-np.sum(lam * np.log(lam)))
+    return float(np.log(np.sum(lam ** alpha)) / (1 - alpha))
+
+
+def renyi_entropy(c: OracleCache, u: int, v: int, alpha: float = 1.0) -> float:
+    """`renyi_entropy(bp_cache, e; α)` (src/entanglement.jl:73-86): ρ = √m2ᵀ·m1·√m2ᵀ from the two messages
+    of the bond (m1 = message(e), m2 = message(reverse(e)), √ via `pseudo_sqrt_inv_sqrt` with the default cutoff)."""
+    m1, m2 = c.message(u, v), c.message(v, u)
+    eps = np.finfo(_real_dtype(c.dtype)).eps
+    r = pseudo_sqrt_inv_sqrt(m2, 10 * eps)[0].astype(_wide(c.dtype))
+    rho = r.T @ m1.astype(_wide(c.dtype)) @ r.T
+    return renyi_entropy_matrix(rho, alpha)
+
+
 def expect_two_site(c: OracleCache, v1: int, v2: int, op1: np.ndarray, op2: np.ndarray, coeff=1.0):
     """Adjacent two-site observable: region {v1,v2} is its own Steiner tree (expect.jl:67)."""
     if coeff == 0:

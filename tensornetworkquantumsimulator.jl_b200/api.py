@@ -544,6 +544,42 @@ def normalize(tns: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Opt
     return bpc.network()
 
 
+def renyi_entropy(bpc: BeliefPropagationCache, edge, alpha: float = 1.0) -> float:
+    """`renyi_entropy(bp_cache, e; α)` (`src/entanglement.jl:73-86`): Rényi entropy across a bond from the two
+    converged messages on it — ρ = √m2ᵀ·m1·√m2ᵀ, normalised by its trace, eigenvalues below 10·eps dropped
+    (`:21-29`).  χ×χ host algebra on `tnqs_get_message`; exact on trees."""
+    a, b = edge
+    m1 = bpc.message((a, b)).astype(np.complex128)
+    m2 = bpc.message((b, a)).astype(np.complex128)
+    eps = np.finfo(np.float32 if bpc.dtype == np.complex64 else np.float64).eps
+    h = m2
+    lam, q = np.linalg.eigh(h)  # lower triangle, as LAPACK heev (safe_eigen, utils.jl:94-108)
+    keep = ~((lam == 0) | (np.abs(lam) < 10 * eps))
+    if np.any(lam[keep] < 0):
+        raise ValueError("DomainError: sqrt of a negative message eigenvalue")
+    f = np.where(keep, np.sqrt(np.where(keep, lam, 0.0)), 0.0)
+    r = (q * f) @ q.conj().T
+    rho = r.T @ m1 @ r.T
+    rho = rho / np.trace(rho)
+    ev = np.linalg.eigvalsh(rho)
+    ev = ev[np.abs(ev) > 10 * eps]  # eps of the state's real type (entanglement.jl:26)
+    if alpha == 1:
+        return float(-np.sum(ev * np.log(ev)))
+    return float(np.log(np.sum(ev ** alpha)) / (1 - alpha))
+
+
+def von_neumann_entanglement_entropy(psi, edge, alg: str = "bp", cache_update_kwargs: Optional[dict] = None,
+                                     device: int = 0) -> float:
+    """`von_neumann_entanglement_entropy(ψ | bpc, e; alg="bp")` (`src/entanglement.jl`): α = 1."""
+    if alg != "bp":
+        raise ArgumentError('von_neumann_entanglement_entropy: only alg="bp" is implemented')
+    if isinstance(psi, TensorNetworkState):
+        bpc = BeliefPropagationCache(psi, device=device)
+        kw = cache_update_kwargs if cache_update_kwargs is not None else default_bp_update_kwargs(bpc)
+        psi = update(bpc, inplace=True, **kw)
+    return renyi_entropy(psi, edge, 1.0)
+
+
 def _collect_observable(obs, g: NamedGraph):
     """`collectobservable` (`expect.jl:159-175`)."""
     coeff = 1 if len(obs) == 2 else obs[-1]

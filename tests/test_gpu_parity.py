@@ -415,3 +415,33 @@ def test_partitionfunction_rescale_normalize(dtype, tol):
     assert abs(np.vdot(full, full) - 1) < 100 * ftol
     full0 = orc.to_statevector(oracle_from_tns(pt))
     assert abs(tq.norm_sqr(pt, alg="bp") - np.vdot(full0, full0)) < 100 * ftol * abs(np.vdot(full0, full0))
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_bond_entropy(dtype, tol):
+    """renyi_entropy(bp_cache, e; α) (src/entanglement.jl:73-86): the GHZ known answer log 2 of
+    /root/reference/test/test_constructors.jl:69-74 on the device path, and a random loopy state vs the oracle."""
+    g = tq.named_grid((3, 3))
+    ts = {}
+    for i, v in enumerate(g.vertices()):
+        z = len(g.incident[i])
+        t = np.zeros((2,) + (2,) * z, dtype=dtype)
+        t[(0,) * (z + 1)] = 1
+        t[(1,) * (z + 1)] = 1
+        ts[v] = t
+    ghz = tq.TensorNetworkState(g, ts, dtype)
+    assert ghz.maxvirtualdim() == 2
+    e0 = g.edges[0]
+    s = tq.von_neumann_entanglement_entropy(ghz, e0, alg="bp")
+    assert abs(s - np.log(2)) < (1e-9 if dtype == np.complex128 else 1e-4)
+    dims = [2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=41)
+    seq = tq.bipartite_edge_sequence(g)
+    bpc = tq.update(tq.BeliefPropagationCache(psi), maxiter=200, tolerance=1e-13 if dtype == np.complex128 else 1e-9,
+                    edge_sequence=seq)
+    c = oracle_from_bpc(bpc)
+    for e in g.edges[:4]:
+        for alpha in (1.0, 2.0):
+            got = tq.renyi_entropy(bpc, e, alpha)
+            want = orc.renyi_entropy(c, g.index[e[0]], g.index[e[1]], alpha)
+            assert abs(got - want) < (1e-9 if dtype == np.complex128 else 1e-3), (e, alpha)

@@ -269,3 +269,29 @@ def test_partitionfunction_exact_on_tree_and_rescale():
     assert abs(orc.partitionfunction(r) - 1) < 1e-12
     p2 = orc.to_statevector(r)
     assert abs(np.vdot(p2, p2) - 1) < 1e-10  # exact on a tree: the rescaled state is normalised
+
+
+def _ghz_tensors(g, dtype=np.complex128):
+    """|0…0⟩ + |1…1⟩ as a bond-dimension-2 TNS: T_v[s, a, b, …] = 1 iff s = a = b = …
+    (the ψ1 + ψ2 of /root/reference/test/test_constructors.jl:69-70)."""
+    ts = []
+    for i in range(g.nv):
+        z = len(g.incident[i])
+        t = np.zeros((2,) + (2,) * z, dtype=dtype)
+        t[(0,) * (z + 1)] = 1
+        t[(1,) * (z + 1)] = 1
+        ts.append(t)
+    return ts
+
+
+@pytest.mark.parametrize("graph", ["path", "grid"])
+def test_ghz_bond_entropy_is_log2(graph):
+    """Known answer of /root/reference/test/test_constructors.jl:69-74:
+    von_neumann_entanglement_entropy(ψGHZ, e; alg="bp") ≈ log 2."""
+    g = tq.named_path_graph(4) if graph == "path" else tq.named_grid((3, 3))
+    c = orc.OracleCache(g.nv, g.edge_uv(), _ghz_tensors(g), np.complex128)
+    seq = [(g.index[a], g.index[b]) for a, b in tq.forest_cover_edge_sequence(g)]
+    c, _ = orc.bp_update(c, seq, maxiter=50, tolerance=1e-12)
+    u, v = g.edge_uv()[0]
+    assert abs(orc.renyi_entropy(c, u, v, 1.0) - math.log(2)) < 1e-10
+    assert abs(orc.renyi_entropy(c, u, v, 2.0) - math.log(2)) < 1e-10

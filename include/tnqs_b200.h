@@ -141,6 +141,12 @@ int  tnqs_vertex_scalars(tnqs_handle h, int n, const int32_t* verts, double* out
  * factors are complex128, each vertex at most once. */
 int  tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* factors /*2*n*/);
 
+/* tn[v] <- tn[v] x_{bond to nbr} M for every listed (v, nbr): M is chi x chi row-major [in][out] complex128,
+ * matrices packed back to back; bond dimensions unchanged.  The device half of symmetric_gauge!
+ * (symmetric_gauge.jl:1-56: psi_src * inv_rootX * U * sqrtS etc.); the chi x chi algebra stays on the host. */
+int  tnqs_apply_leg_matrices(tnqs_handle h, int n, const int32_t* verts, const int32_t* nbrs,
+                             const double* mats);
+
 /* --- multi-GPU: vertex ownership + NCCL exchange --------------------------- */
 
 /* Join an NCCL communicator: every rank holds the full graph, owns the site tensors of the

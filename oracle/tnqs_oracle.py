@@ -473,6 +473,46 @@ def rescale(c: OracleCache) -> OracleCache:
     return c
 
 
+def symmetric_gauge_factors(mx: np.ndarray, my: np.ndarray, regularization: float):
+    """The χ×χ algebra of one edge of `symmetric_gauge!` (src/symmetric_gauge.jl:12-40): from
+    mx = message(src→dst), my = message(dst→src) return (X_src, X_dst, S) with
+    ψ_src ← ψ_src ×_e X_src, ψ_dst ← ψ_dst ×_e X_dst, both new messages = diag(S).
+    X_src = X^{-1/2}·U·√S, X_dst = Y^{-1/2}·conj(V)·√S where X^{1/2}·(Y^{1/2})ᵀ = U·S·V†."""
+    # ITensors' `eigen` reads a tensor on (l, l') as the map l → l', i.e. as the matrix m[bra, ket] = mᵀ of our
+    # m[ket, bra] storage; with m itself the transformed messages would only be symmetric for real messages
+    # (derivation in tests/test_oracle.py::test_symmetric_gauge_…: the fixed point must survive the regauging).
+    xd, xu = np.linalg.eigh(np.asarray(mx, dtype=np.complex128).T)
+    yd, yu = np.linalg.eigh(np.asarray(my, dtype=np.complex128).T)
+    xd = xd + regularization
+    yd = yd + regularization
+    if np.any(xd < 0) or np.any(yd < 0):
+        raise ValueError("DomainError: sqrt of a negative message eigenvalue")
+    root_x = (xu * np.sqrt(xd)) @ xu.conj().T
+    root_y = (yu * np.sqrt(yd)) @ yu.conj().T
+    inv_root_x = (xu / np.sqrt(xd)) @ xu.conj().T
+    inv_root_y = (yu / np.sqrt(yd)) @ yu.conj().T
+    ce = root_x @ root_y.T
+    u, sv, vh = np.linalg.svd(ce)
+    v = vh.conj().T
+    x_src = inv_root_x @ u * np.sqrt(sv)
+    x_dst = inv_root_y @ v.conj() * np.sqrt(sv)
+    return x_src, x_dst, sv
+
+
+def symmetric_gauge(c: OracleCache, regularization: Optional[float] = None) -> OracleCache:
+    """`symmetric_gauge(bp_cache)` (src/symmetric_gauge.jl:1-56), no SVD truncation keywords."""
+    c = c.copy()
+    if regularization is None:
+        regularization = 10 * np.finfo(_real_dtype(c.dtype)).eps
+    for (a, b) in c.edges:
+        x_src, x_dst, sv = symmetric_gauge_factors(c.message(a, b), c.message(b, a), regularization)
+        c.T[a] = np.ascontiguousarray(_absorb(c.T[a].astype(np.complex128), x_src, c.leg(a, b)), dtype=c.dtype)
+        c.T[b] = np.ascontiguousarray(_absorb(c.T[b].astype(np.complex128), x_dst, c.leg(b, a)), dtype=c.dtype)
+        c.msg[(a, b)] = np.diag(sv).astype(c.dtype)
+        c.msg[(b, a)] = np.diag(sv).astype(c.dtype)
+    return c
+
+
 def renyi_entropy_matrix(rho: np.ndarray, alpha: float, normalize: bool = True) -> float:
     """`renyi_entropy(ρ::AbstractMatrix, α)` (src/entanglement.jl:21-29)."""
     rho = np.asarray(rho)

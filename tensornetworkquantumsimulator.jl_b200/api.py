@@ -544,6 +544,62 @@ def normalize(tns: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Opt
     return bpc.network()
 
 
+def _symmetric_gauge_factors(mx: np.ndarray, my: np.ndarray, regularization: float):
+    """χ×χ algebra of one edge of `symmetric_gauge!` (`src/symmetric_gauge.jl:12-40`): returns (X_src, X_dst, S)
+    with ψ_src ← ψ_src ×_e X_src, ψ_dst ← ψ_dst ×_e X_dst and both new messages diag(S).  ITensors' `eigen` reads
+    a message on (l, l') as the map l → l', i.e. as the transpose of the m[ket, bra] storage used here."""
+    xd, xu = np.linalg.eigh(np.asarray(mx, dtype=np.complex128).T)
+    yd, yu = np.linalg.eigh(np.asarray(my, dtype=np.complex128).T)
+    xd = xd + regularization
+    yd = yd + regularization
+    if np.any(xd < 0) or np.any(yd < 0):
+        raise ValueError("DomainError: sqrt of a negative message eigenvalue")
+    root_x = (xu * np.sqrt(xd)) @ xu.conj().T
+    root_y = (yu * np.sqrt(yd)) @ yu.conj().T
+    inv_root_x = (xu / np.sqrt(xd)) @ xu.conj().T
+    inv_root_y = (yu / np.sqrt(yd)) @ yu.conj().T
+    u, sv, vh = np.linalg.svd(root_x @ root_y.T)
+    return inv_root_x @ u * np.sqrt(sv), inv_root_y @ vh.T * np.sqrt(sv), sv
+
+
+def symmetric_gauge(x, regularization: Optional[float] = None, cache_update_kwargs: Optional[dict] = None,
+                    inplace: bool = False, device: int = 0):
+    """`symmetric_gauge(bp_cache | tns; regularization)` (`src/symmetric_gauge.jl:1-68`), without SVD truncation
+    keywords: every bond is regauged so that its two messages become the same diagonal matrix.  The χ×χ
+    eigen/SVD algebra runs on the host (NumPy/LAPACK, as the reference runs it on the CPU); the site tensors are
+    updated on the device in one batched `tnqs_apply_leg_matrices` call (edges touch disjoint legs)."""
+    if isinstance(x, TensorNetworkState):
+        bpc = BeliefPropagationCache(x, device=device)
+        kw = cache_update_kwargs if cache_update_kwargs is not None else dict(maxiter=40)
+        bpc = update(bpc, inplace=True, **kw)
+        return symmetric_gauge(bpc, regularization=regularization, inplace=True).network()
+    out = x if inplace else x.copy()
+    g = out.graph
+    if regularization is None:
+        regularization = 10 * np.finfo(np.float32 if out.dtype == np.complex64 else np.float64).eps
+    verts, nbrs, mats, new_msgs = [], [], [], []
+    for (a, b) in g.edges:
+        xs, xd_, sv = _symmetric_gauge_factors(out.message((a, b)), out.message((b, a)), regularization)
+        verts += [g.index[a], g.index[b]]
+        nbrs += [g.index[b], g.index[a]]
+        mats += [np.ascontiguousarray(xs, dtype=np.complex128).reshape(-1), np.ascontiguousarray(xd_, dtype=np.complex128).reshape(-1)]
+        new_msgs.append(((a, b), np.diag(sv)))
+    if verts:
+        v_a, v_p = _i32(np.array(verts, dtype=np.int32))
+        n_a, n_p = _i32(np.array(nbrs, dtype=np.int32))
+        m = np.ascontiguousarray(np.concatenate(mats)).view(np.float64)
+        _lib.check(out._lib.tnqs_apply_leg_matrices(out._h, len(verts), v_p, n_p, m.ctypes.data_as(C.POINTER(C.c_double))))
+    for (a, b), s_ in new_msgs:
+        out.setmessage((a, b), s_)
+        out.setmessage((b, a), s_)
+    return out
+
+
+def symmetrize_and_normalize(bpc: BeliefPropagationCache, **kwargs) -> BeliefPropagationCache:
+    """`symmetrize_and_normalize` (`src/symmetric_gauge.jl:70-74`): rescale, then symmetric gauge."""
+    return symmetric_gauge(rescale(bpc), inplace=True, **kwargs)
+
+
 def renyi_entropy(bpc: BeliefPropagationCache, edge, alpha: float = 1.0) -> float:
     """`renyi_entropy(bp_cache, e; α)` (`src/entanglement.jl:73-86`): Rényi entropy across a bond from the two
     converged messages on it — ρ = √m2ᵀ·m1·√m2ᵀ, normalised by its trace, eigenvalues below 10·eps dropped

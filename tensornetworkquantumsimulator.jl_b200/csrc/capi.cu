@@ -143,6 +143,12 @@ int tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* f
     E(h).scale_sites(n, verts, factors);
   });
 }
+int tnqs_apply_leg_matrices(tnqs_handle h, int n, const int32_t* verts, const int32_t* nbrs, const double* mats) {
+  return guarded([&] {
+    if (n > 0 && (!verts || !nbrs || !mats)) throw Error(TNQS_EINVAL, "null argument");
+    E(h).apply_leg_matrices(n, verts, nbrs, mats);
+  });
+}
 int tnqs_expect_two_site(tnqs_handle h, int nobs, const int32_t* verts, const double* op_mats, double* out) {
   return guarded([&] {
     if (nobs > 0 && (!verts || !op_mats || !out)) throw Error(TNQS_EINVAL, "null argument");

@@ -2035,6 +2035,47 @@ void Engine::scale_sites(int n, const int32_t* verts, const double* factors) {
   TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
+// tn[v] ← tn[v] ×_{leg(v,nbr)} M for a list of (v, nbr, M): M is χ×χ row-major [in][out] complex128.  Bond
+// dimensions do not change.  Used by symmetric_gauge (symmetric_gauge.jl:1-56) and other host-driven regauging.
+void Engine::apply_leg_matrices(int n, const int32_t* verts, const int32_t* nbrs, const double* mats) {
+  if (n <= 0) return;
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  std::map<int, int> chain_of;
+  std::vector<Chain> chains;
+  std::set<std::pair<int, int>> seen;
+  size_t off = 0;
+  for (int i = 0; i < n; ++i) {
+    const int v = verts[i], w = nbrs[i];
+    const int de = dedge(w, v);  // validates adjacency
+    if (!seen.insert({v, w}).second) throw Error(TNQS_EINVAL, "tnqs_apply_leg_matrices: a (vertex, neighbour) pair may appear only once");
+    const int chi = bond_[de / 2];
+    const size_t cnt = (size_t)chi * chi;
+    void* dm = talloc(cnt * esz_);
+    if (c64()) {
+      std::vector<float2> h(cnt);
+      for (size_t k = 0; k < cnt; ++k) { h[k].x = (float)mats[off + 2 * k]; h[k].y = (float)mats[off + 2 * k + 1]; }
+      TNQS_CUDA(cudaMemcpyAsync(dm, h.data(), cnt * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));  // h is a pageable temporary
+    } else {
+      TNQS_CUDA(cudaMemcpyAsync(dm, mats + off, cnt * sizeof(double2), cudaMemcpyHostToDevice, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));
+    }
+    off += 2 * cnt;
+    auto f = chain_of.find(v);
+    if (f == chain_of.end()) { f = chain_of.emplace(v, (int)chains.size()).first; chains.emplace_back(); chains.back().v = v; }
+    chains[f->second].steps.push_back({leg_pos(v, de / 2), dm});
+  }
+  run_chains(chains);
+  for (auto& c : chains) {
+    if (!owns(c.v) || c.steps.empty() || !c.result) continue;
+    TNQS_CUDA(cudaMemcpyAsync(site_[c.v], c.result, (size_t)site_elems(c.v) * esz_, cudaMemcpyDeviceToDevice, stream_));
+  }
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+  release_slabs();
+}
+
 void Engine::expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out) {
   TNQS_CUDA(cudaSetDevice(device_));
   check_shapes();

@@ -445,3 +445,29 @@ def test_bond_entropy(dtype, tol):
             got = tq.renyi_entropy(bpc, e, alpha)
             want = orc.renyi_entropy(c, g.index[e[0]], g.index[e[1]], alpha)
             assert abs(got - want) < (1e-9 if dtype == np.complex128 else 1e-3), (e, alpha)
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_symmetric_gauge(dtype, tol):
+    """symmetric_gauge (src/symmetric_gauge.jl:1-56) on the device path: the state is unchanged, both messages of
+    every bond become the same diagonal matrix, equal to the oracle's, and remain the BP fixed point."""
+    ftol = tol if dtype == np.complex128 else 10 * tol
+    g = tq.named_grid((3, 2))
+    dims = [2, 3, 2, 3, 2, 3, 2][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=51)
+    seq = tq.bipartite_edge_sequence(g)
+    bpc = tq.update(tq.BeliefPropagationCache(psi), maxiter=500, tolerance=1e-14 if dtype == np.complex128 else 1e-10,
+                    edge_sequence=seq)
+    c = oracle_from_bpc(bpc)
+    sg = tq.symmetric_gauge(bpc)
+    so = orc.symmetric_gauge(c)
+    ov, n1, n2 = state_overlap(oracle_from_bpc(sg), c)
+    assert abs(ov - 1) < 100 * ftol and abs(n1 / n2 - 1) < 100 * ftol
+    for (a, b) in g.edges:
+        m1, m2 = sg.message((a, b)), sg.message((b, a))
+        assert np.array_equal(m1, m2)
+        assert rel(np.diag(m1), np.diag(so.msg[(g.index[a], g.index[b])])) < 100 * ftol
+    again = tq.update(sg, maxiter=1, tolerance=None, edge_sequence=seq)
+    for (a, b) in g.edges:
+        x, y = again.message((a, b)).astype(np.complex128), sg.message((a, b)).astype(np.complex128)
+        assert rel(x / np.trace(x), y / np.trace(y)) < (1e-6 if dtype == np.complex128 else 1e-3)

@@ -295,3 +295,23 @@ def test_ghz_bond_entropy_is_log2(graph):
     u, v = g.edge_uv()[0]
     assert abs(orc.renyi_entropy(c, u, v, 1.0) - math.log(2)) < 1e-10
     assert abs(orc.renyi_entropy(c, u, v, 2.0) - math.log(2)) < 1e-10
+
+
+def test_symmetric_gauge_keeps_state_and_symmetrises_messages():
+    """symmetric_gauge (src/symmetric_gauge.jl:1-56): a pure gauge transformation — the physical state is
+    unchanged, both messages of every edge become the same diagonal matrix, and they stay a BP fixed point."""
+    g = tq.named_grid((3, 2))
+    c = orc.random_state(g.nv, g.edge_uv(), 2, 3, np.complex128, seed=9)
+    seq = [(g.index[a], g.index[b]) for a, b in tq.bipartite_edge_sequence(g)]
+    c, rep = orc.bp_update(c, seq, maxiter=500, tolerance=1e-14)
+    s = orc.symmetric_gauge(c)
+    p1, p2 = orc.to_statevector(c), orc.to_statevector(s)
+    ov = abs(np.vdot(p1, p2)) / (np.linalg.norm(p1) * np.linalg.norm(p2))
+    assert abs(ov - 1) < 1e-9
+    for (a, b) in s.edges:
+        m1, m2 = s.message(a, b), s.message(b, a)
+        assert np.allclose(m1, m2) and np.allclose(m1, np.diag(np.diag(m1)))
+    s2, rep2 = orc.bp_update(s, seq, maxiter=1, tolerance=None)
+    for (a, b) in s.edges:  # still the fixed point (up to normalisation)
+        x, y = s2.message(a, b), s.message(a, b)
+        assert np.allclose(x / np.trace(x), y / np.trace(y), atol=1e-7)

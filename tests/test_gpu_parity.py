@@ -471,3 +471,25 @@ def test_symmetric_gauge(dtype, tol):
     for (a, b) in g.edges:
         x, y = again.message((a, b)).astype(np.complex128), sg.message((a, b)).astype(np.complex128)
         assert rel(x / np.trace(x), y / np.trace(y)) < (1e-6 if dtype == np.complex128 else 1e-3)
+
+
+def test_device_matches_golden_config1():
+    """BASELINE config 1 against the committed golden vectors (tests/golden/, minted by the oracle): per-gate
+    truncation errors, bond dimension and ⟨Z⟩ on every vertex for 4 layers; layer 1 also has the analytic
+    value ⟨Z⟩ = cos(0.5)."""
+    import json
+    import os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                       "config1_5x5_tfim_maxdim4_c128.json")))
+    g = tq.named_grid((5, 5))
+    layer = tfim_layer(g)
+    kw = dict(maxdim=4, cutoff=1e-10, normalize_tensors=False)
+    psi = tq.BeliefPropagationCache(tq.tensornetworkstate(np.complex128, lambda v: "↑", g, "S=1/2"))
+    for l, ref in enumerate(gold["layers"]):
+        psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw)
+        assert psi.maxvirtualdim() == ref["maxvirtualdim"]
+        zs = np.real(np.array(tq.expect(psi, [("Z", [v]) for v in g.vertices()])))
+        assert np.max(np.abs(zs - np.array(ref["sz_all"]))) < 1e-7, l
+        assert np.max(np.abs(errs - np.array(ref["trunc_err"]))) < 1e-7 * max(1.0, ref["max_trunc_err"] / 1e-3), l
+        if l == 0:
+            assert abs(zs[g.index[(3, 3)]] - np.cos(0.5)) < 1e-12

@@ -315,3 +315,22 @@ def test_symmetric_gauge_keeps_state_and_symmetrises_messages():
     for (a, b) in s.edges:  # still the fixed point (up to normalisation)
         x, y = s2.message(a, b), s.message(a, b)
         assert np.allclose(x / np.trace(x), y / np.trace(y), atol=1e-7)
+
+
+def test_oracle_reproduces_golden_config1():
+    """tests/golden/config1_…json (minted by tests/golden/make_golden.py) pins the oracle against drift; layer 1
+    has an analytic answer: ⟨Z⟩ = cos(2·hx·dt) = cos(0.5) (Rx on |↑⟩, Rz and Rzz commute with Z)."""
+    import json
+    import os
+    sys_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(sys_path, "config1_5x5_tfim_maxdim4_c128.json")))
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(sys_path, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    now = mg.config1(nlayers=3)
+    assert abs(gold["layers"][0]["sz_center"] - math.cos(0.5)) < 1e-12
+    for a, b in zip(now["layers"], gold["layers"]):
+        assert a["maxvirtualdim"] == b["maxvirtualdim"]
+        assert np.allclose(a["sz_all"], b["sz_all"], atol=1e-10)
+        assert np.allclose(a["trunc_err"], b["trunc_err"], rtol=1e-6, atol=1e-13)

@@ -203,9 +203,20 @@ def run_ours(args):
     seq = tq.bipartite_edge_sequence(g) if args.schedule == "bipartite" else tq.forest_cover_edge_sequence(g)
     kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
     bp = dict(maxiter=25, tolerance=1e-5, edge_sequence=seq)  # default_bp_update_kwargs for ComplexF32
-    psi = tq.BeliefPropagationCache(tq.tensornetworkstate(dtype, lambda v: "↑", g, "S=1/2"), device=local)
+    if args.random_state:
+        # BASELINE config 5: synthetic random TNS with every bond = χ (iid normal entries, seed 1234, each tensor
+        # scaled to unit Frobenius norm), one BP update; no evolution from the product state
+        tns = tq.random_tensornetworkstate(dtype, g, bond_dimension=chi, seed=1234)
+        for v in list(tns.tensors):
+            tns.tensors[v] = (tns.tensors[v] / np.linalg.norm(tns.tensors[v])).astype(dtype)
+        psi = tq.BeliefPropagationCache(tns, device=local)
+        del tns
+    else:
+        psi = tq.BeliefPropagationCache(tq.tensornetworkstate(dtype, lambda v: "↑", g, "S=1/2"), device=local)
     if world > 1:
         tq.shard(psi)  # row strips of the lattice, one per rank; messages / Gram matrices travel over NCCL
+    if args.random_state:
+        psi = tq.update(psi, inplace=True, **bp)
     obs = ("Z", [(L // 2 + 1, L // 2 + 1)])
 
     def sync_all():
@@ -214,7 +225,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     t_prep = time.perf_counter()
-    for _ in range(args.prep):
+    nprep = args.prep if args.prep is not None else (0 if args.random_state else 15)
+    for _ in range(nprep):
         psi, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True)
     for _ in range(args.warmup):  # same call as the timed steps (functional copy): warms the memory pools of that path
         psi, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=args.inplace)
@@ -303,7 +315,7 @@ def run_ours(args):
         "config": {"workload": f"{L}x{L} square-lattice TFIM (examples/2dIsing_dynamics.jl constants), maxdim={chi}, "
                                f"cutoff=1e-10, ComplexF32, one Trotter layer per step = {n_two} two-site + {2*g.nv} one-site "
                                f"gates + {ncol+1} BP refreshes",
-                   "prep_layers": args.prep, "bond_dim_min_mean_max": [int(bd.min()), float(bd.mean()), int(bd.max())],
+                   "prep_layers": nprep, "initial_state": ("random TNS, all bonds = chi, seed 1234" if args.random_state else "product state |↑…↑>"), "bond_dim_min_mean_max": [int(bd.min()), float(bd.mean()), int(bd.max())],
                    "bp_schedule": args.schedule, "bp_sweeps_per_layer": sweeps_per_layer,
                    "sharding": ("none" if world == 1 else f"vertex row-strips over {world} ranks; NCCL: broadcast of level messages + Gram matrices, all-gather of the per-gate factorisation results (gate k solved on rank k mod {world})"),
                    "l2": "inputs larger than L2 (state %.2f GB)" % (sum(2 * int(np.prod([2] + [bd[e] for e, _ in g.incident[i]])) * 4
@@ -330,7 +342,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--L", type=int, default=16)
     ap.add_argument("--chi", type=int, default=32)
-    ap.add_argument("--prep", type=int, default=15, help="untimed layers from the product state before warm-up")
+    ap.add_argument("--prep", type=int, default=None, help="untimed layers before warm-up (default: 15 from the product state, 0 with --random-state)")
+    ap.add_argument("--random-state", action="store_true", help="start from a synthetic random TNS with all bonds = chi (BASELINE config 5) instead of evolving the product state")
     ap.add_argument("--schedule", default="bipartite", choices=["bipartite", "forest"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--inplace", action="store_true", help="diagnostic: mutate the cache instead of the reference's functional copy")

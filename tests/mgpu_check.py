@@ -1,7 +1,7 @@
-"""torchrun --nproc-per-node 2 tools/mgpu_check.py : sharded run vs the CPU oracle (small lattice)."""
+"""torchrun --nproc-per-node 2 tests/mgpu_check.py : sharded run vs the CPU oracle (small lattice)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import numpy as np
 import torch
 import torch.distributed as dist

@@ -1001,17 +1001,26 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
 #define TNQS_JAC(L, R) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
     else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
     else launch_jacobi_cluster<L, R, 512, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); } while (0)
-    if (LPP == 16) {
-      if (RPL <= 1) TNQS_JAC(16, 1);
-      else if (RPL == 2) TNQS_JAC(16, 2);
-      else if (RPL == 4) TNQS_JAC(16, 4);
-      else TNQS_JAC(16, 8);
-    } else {
-      if (RPL <= 2) TNQS_JAC(32, 2);
-      else if (RPL == 4) TNQS_JAC(32, 4);
-      else TNQS_JAC(32, 8);
+    bool launched = true;
+    try {
+      if (LPP == 16) {
+        if (RPL <= 1) TNQS_JAC(16, 1);
+        else if (RPL == 2) TNQS_JAC(16, 2);
+        else if (RPL == 4) TNQS_JAC(16, 4);
+        else TNQS_JAC(16, 8);
+      } else {
+        if (RPL <= 2) TNQS_JAC(32, 2);
+        else if (RPL == 4) TNQS_JAC(32, 4);
+        else TNQS_JAC(32, 8);
+      }
+    } catch (const Error&) {
+      // a cluster shape the device refuses (launch errors are synchronous): the global-memory kernel below
+      // factorises the same task table
+      cudaGetLastError();
+      launched = false;
     }
 #undef TNQS_JAC
+    if (launched) {
     count_launch();
     TNQS_CUDA(cudaGetLastError());
     const bool dbg = std::getenv("TNQS_JACOBI_DEBUG") != nullptr;
@@ -1025,6 +1034,7 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
                    nb, maxn, maxmt, LPP, RPL, BC, C, smem, mn, avg / nb, mx);
     }
     return;
+    }
   }
   const int pairs = (maxn + 1) / 2;
   const int maxwarps = maxm <= 128 ? 32 : (maxm <= 256 ? 16 : 8);  // register budget per lane grows with m

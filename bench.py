@@ -292,7 +292,7 @@ def run_ours(args):
     nl = sp["mode_launches"] if fam[0] == "mode_product" else sp["gram_launches"]
     ach = by / (fam[1] * 1e-3) / 1e9 if fam[1] > 0 else 0.0
     roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
-            "traffic": None, "traffic_note": "ncu --set full (profiles/r1s_prof_tc_mode_raw.csv): dram read+write of a tc_mode launch = 1.00x its algorithmic bytes",
+            "traffic": None, "traffic_note": "ncu --set full of the 8x8 run (profiles/r1s_prof_tc_mode_raw.csv): a tc_mode launch moves 0.758 GB read + 0.856 GB written in DRAM; its output (= input) size is 0.856 GB, i.e. no re-reads (reads 11 % below the algorithmic bytes: L2 hits on lines the previous launch wrote)",
             "kernel": ("tc_mode_kernel (tcgen05 3xTF32)" if fam[0] == "mode_product" else "tc_gram_kernel (tcgen05 3xTF32)"),
             "launches": int(nl), "peak_source": pk["source"],
             "algorithmic_tflops": fl / (fam[1] * 1e-3) / 1e12 if fam[1] > 0 else 0.0,

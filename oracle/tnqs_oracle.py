@@ -564,6 +564,71 @@ def expect_two_site(c: OracleCache, v1: int, v2: int, op1: np.ndarray, op2: np.n
 # dense contraction for small systems (test helper: `norm_sqr(ψ; alg="exact")` etc.)
 # ---------------------------------------------------------------------------------------------
 
+def steiner_path(c: OracleCache, v1: int, v2: int) -> List[int]:
+    """Vertices of a shortest path v1 … v2 (BFS, neighbours in incidence order).  For two vertices the Steiner
+    tree of expect.jl:67 is a shortest path; it is unique on trees (on loopy graphs the reference's choice among
+    equal-length paths is an implementation detail of Graphs.steiner_tree)."""
+    prev = {v1: -1}
+    queue = [v1]
+    while queue:
+        x = queue.pop(0)
+        if x == v2:
+            break
+        for _, w in c.incident[x]:
+            if w not in prev:
+                prev[w] = x
+                queue.append(w)
+    path = [v2]
+    while path[-1] != v1:
+        path.append(prev[path[-1]])
+    return path[::-1]
+
+
+def expect_region(c: OracleCache, region: Sequence[int], ops: Dict[int, np.ndarray], coeff=1.0):
+    """`expect(Algorithm"bp", cache, obs)` for a multi-site observable (src/expect.jl:59-82): the tensors of the
+    Steiner-tree region, their conjugates, the operators and the messages entering the region, contracted
+    exactly; numerator / denominator.  `region` must be connected; dense contraction (small regions only)."""
+    if coeff == 0:
+        return 0.0
+    region = list(region)
+    inside = set(region)
+    wide = _wide(c.dtype)
+    # region state: axes = [phys of every region vertex..., external legs...]; internal bonds contracted
+    letters = iter("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ")
+    bond_letter: Dict[int, str] = {}
+    phys_letter: Dict[int, str] = {}
+    ext: List[Tuple[str, int, int]] = []  # (letter, inside vertex, outside neighbour)
+    subs = []
+    for v in region:
+        phys_letter[v] = next(letters)
+        sub = phys_letter[v]
+        for e, w in c.incident[v]:
+            if w in inside:
+                if e not in bond_letter:
+                    bond_letter[e] = next(letters)
+                sub += bond_letter[e]
+            else:
+                l = next(letters)
+                ext.append((l, v, w))
+                sub += l
+        subs.append(sub)
+    out_sub = "".join(phys_letter[v] for v in region) + "".join(l for l, _, _ in ext)
+    psi = np.einsum(",".join(subs) + "->" + out_sub, *[c.T[v].astype(wide) for v in region], optimize=True)
+    n = len(region)
+    # absorb the incoming messages on the ket side of every external leg: m[ket, bra]
+    ket = psi
+    for k, (_, v, w) in enumerate(ext):
+        ket = np.moveaxis(np.tensordot(ket, c.message(w, v).astype(wide), axes=([n + k], [0])), -1, n + k)
+    dims = psi.shape[:n]
+    kmat = ket.reshape(int(np.prod(dims)), -1)
+    bmat = psi.reshape(int(np.prod(dims)), -1).conj()
+    rho = kmat @ bmat.T  # ρ[s, s'] = Σ_ext ket[s, ext'] conj(ψ)[s', ext']
+    op = np.ones((1, 1), dtype=wide)
+    for v in region:
+        op = np.kron(op, np.asarray(ops.get(v, np.eye(c.T[v].shape[0])), dtype=wide))
+    return coeff * np.sum(op * rho.T) / np.trace(rho)
+
+
 def to_statevector(c: OracleCache) -> np.ndarray:
     """Contract the whole TNS into a dense vector ψ[s_0, …, s_{nv-1}] (small systems only)."""
     letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"

@@ -334,3 +334,27 @@ def test_oracle_reproduces_golden_config1():
         assert a["maxvirtualdim"] == b["maxvirtualdim"]
         assert np.allclose(a["sz_all"], b["sz_all"], atol=1e-10)
         assert np.allclose(a["trunc_err"], b["trunc_err"], rtol=1e-6, atol=1e-13)
+
+
+def test_multi_site_expect_exact_on_tree():
+    """expect(alg="bp") for non-adjacent vertices (src/expect.jl:59-82, Steiner-tree region) is exact on a tree:
+    compared with the dense state vector (the reference's test_expect.jl:26-30 flavour)."""
+    g = tq.named_comb_tree((3, 2))
+    c = orc.random_state(g.nv, g.edge_uv(), 2, 2, np.complex128, seed=13)
+    seq = [(g.index[a], g.index[b]) for a, b in tq.forest_cover_edge_sequence(g)]
+    c, _ = orc.bp_update(c, seq, maxiter=1, tolerance=None)
+    psi = orc.to_statevector(c).reshape(-1)
+    nrm = np.vdot(psi, psi)
+    Zm, Xm = np.diag([1.0, -1.0]).astype(complex), np.array([[0, 1], [1, 0]], dtype=complex)
+    for (u, v, o1, o2) in ((0, g.nv - 1, Zm, Xm), (1, 4, Xm, Xm), (2, 3, Zm, Zm)):
+        region = orc.steiner_path(c, u, v)
+        assert region[0] == u and region[-1] == v
+        got = orc.expect_region(c, region, {u: o1, v: o2})
+        full = np.ones((1, 1), dtype=complex)
+        for i in range(g.nv):
+            full = np.kron(full, o1 if i == u else (o2 if i == v else np.eye(2)))
+        want = np.vdot(psi, full @ psi) / nrm
+        assert abs(got - want) < 1e-10, (u, v)
+    # adjacent pair: agrees with the dedicated two-site routine
+    (a, b) = g.edge_uv()[0]
+    assert abs(orc.expect_region(c, [a, b], {a: Zm, b: Zm}) - orc.expect_two_site(c, a, b, Zm, Zm)) < 1e-12

@@ -176,6 +176,7 @@ typedef struct {
                                          (device time bp_ms + su_ms below it means the host is the limit) */
   double  sync_ms;                    /* part of wall_ms the host spent blocked waiting for the device;
                                          wall_ms - sync_ms = host preparation / enqueue time               */
+  int64_t tma_launches;               /* of tc_launches: the TMA-fed warp-specialised kernel (kernels_tc2.cuh) */
 } tnqs_stats;
 int  tnqs_get_stats(tnqs_handle h, tnqs_stats* out, int reset);
 int  tnqs_set_profiling(tnqs_handle h, int on);

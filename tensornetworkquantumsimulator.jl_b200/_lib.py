@@ -32,7 +32,8 @@ class Stats(C.Structure):
                 ("mode_ms", C.c_double), ("gram_ms", C.c_double), ("small_ms", C.c_double),
                 ("mode_flops", C.c_double), ("gram_flops", C.c_double),
                 ("mode_launches", C.c_int64), ("gram_launches", C.c_int64), ("tc_launches", C.c_int64),
-                ("mode_bytes", C.c_double), ("gram_bytes", C.c_double), ("wall_ms", C.c_double), ("sync_ms", C.c_double)]
+                ("mode_bytes", C.c_double), ("gram_bytes", C.c_double), ("wall_ms", C.c_double), ("sync_ms", C.c_double),
+                ("tma_launches", C.c_int64)]
 
 
 class TnqsError(RuntimeError):

@@ -98,6 +98,31 @@ struct SlabPool {
 };
 }  // namespace
 
+// Opt-in to > 48 KB dynamic shared memory for every kernel that needs it.  The attribute is per device, so it is
+// tracked per device ordinal (a second cache on another GPU of the same process must opt in again).
+static void ensure_kernel_attributes(int device) {
+  static std::mutex mu;
+  static bool done[64] = {false};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device >= 0 && device < 64 && done[device]) return;
+  auto set = [](const void* f, int bytes) { TNQS_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); };
+  set((const void*)tc::tc_mode_kernel<false>, 200 * 1024);
+  set((const void*)tc::tc_mode_kernel<true>, 200 * 1024);
+  set((const void*)tc2::tc2_mode_kernel<false>, 225 * 1024);
+  set((const void*)tc2::tc2_mode_kernel<true>, 225 * 1024);
+  set((const void*)tc::tc_gram_kernel<false, 1, 2>, 200 * 1024);
+  set((const void*)tc::tc_gram_kernel<false, 2, 2>, 200 * 1024);
+  set((const void*)tc::tc_gram_kernel<true, 1, 2>, 200 * 1024);
+  set((const void*)tc::tc_gram_kernel<true, 2, 2>, 200 * 1024);
+  set((const void*)tc::tc_gram_kernel<true, 4, 1>, 200 * 1024);
+  set((const void*)gram_dmma_kernel<float, false>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, true>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, false>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, true>, 160 * 1024);
+  set((const void*)chol_prepare_kernel, 160 * 1024);
+  if (device >= 0 && device < 64) done[device] = true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // construction / destruction
 // ------------------------------------------------------------------------------------------------
@@ -111,6 +136,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
     throw Error(TNQS_ENOGPU, "no CUDA device visible: tnqs_b200 has no CPU fallback");
   if (device < 0 || device >= ndev) throw Error(TNQS_EINVAL, "bad CUDA device ordinal");
   TNQS_CUDA(cudaSetDevice(device));
+  ensure_kernel_attributes(device);
   eu_.resize(ne); ev_.resize(ne); bond_.resize(ne); phys_.assign(phys, phys + nv);
   inc_.assign(nv, {});
   std::set<std::pair<int, int>> seen;
@@ -141,6 +167,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
   { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_TC2"); use_tc2_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_FAST_SVD"); use_fast_svd_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_CHOL"); use_chol_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_DMMA"); use_dmma_ = !(e && e[0] == '0'); }
@@ -172,6 +199,7 @@ Engine::Engine(const Engine& o)
     : dtype_(o.dtype_), esz_(o.esz_), device_(o.device_), nv_(o.nv_), ne_(o.ne_), eu_(o.eu_), ev_(o.ev_),
       phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
   use_tc_ = o.use_tc_;
+  use_tc2_ = o.use_tc2_;
   use_cluster_jacobi_ = o.use_cluster_jacobi_;
   use_dmma_ = o.use_dmma_;
   use_chol_ = o.use_chol_;
@@ -179,6 +207,7 @@ Engine::Engine(const Engine& o)
   profiling_ = o.profiling_;
   comm_ = o.comm_; owner_ = o.owner_; rank_ = o.rank_; nranks_ = o.nranks_;
   TNQS_CUDA(cudaSetDevice(device_));
+  ensure_kernel_attributes(device_);
   TNQS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   TNQS_CUDA(cudaEventCreate(&ev0_));
   TNQS_CUDA(cudaEventCreate(&ev1_));
@@ -595,14 +624,42 @@ static void launch_mode_variant(const ModeTask* d, int ntasks, int maxtiles, boo
 }
 
 // tcgen05 path for ComplexF32 mode products (kernels_tc.cuh).  Returns the tasks it did not take.
-std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks) {
+std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks_all) {
   std::vector<ModeTask> rest;
-  if (!c64() || !use_tc_) return tasks;
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNQS_CUDA(cudaFuncSetAttribute(tc::tc_mode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    TNQS_CUDA(cudaFuncSetAttribute(tc::tc_mode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+  if (!c64() || !use_tc_) return tasks_all;
+  // ---- TMA-fed warp-specialised kernel (kernels_tc2.cuh) first; what it does not take goes to the older tcgen05 kernel ----
+  std::vector<ModeTask> tasks;
+  if (use_tc2_) {
+    tc2::Plan plan;
+    std::map<tc2::ImageKey, float*> images2;
+    for (auto& t : tasks_all) {
+      tc2::ModeShape ms{t.in, t.out, t.mat, t.ips, t.ops, t.chi_in, t.chi_out, t.KK, t.MM, t.outer, t.inner, t.CC};
+      if (!tc2::plan_add(plan, ms, [&](size_t b) { return talloc(b); }, images2)) tasks.push_back(t);
+    }
+    if (!plan.empty()) {
+      if (!tc2::plan_finish(plan)) throw Error(TNQS_ECUDA, "tc2 mode product: shared-memory plan failed");
+      tc2::PrepTask2* dp = upload(plan.preps);
+      if (!plan.preps.empty()) {
+        tc2::tc2_prep_kernel<<<(unsigned)plan.preps.size(), 256, 0, stream_>>>(dp);
+        count_launch();
+      }
+      for (int g = 0; g < 2; ++g) {
+        if (plan.tasks[g].empty()) continue;
+        tc2::ModeTask2* dt = upload(plan.tasks[g]);
+        tc2::Item* di = upload(plan.items[g]);
+        if (g == 0) tc2::tc2_mode_kernel<false><<<plan.grid[g], tc2::T2_THREADS, plan.smem[g], stream_>>>(dt, di, (int)plan.items[g].size(), plan.geom[g]);
+        else tc2::tc2_mode_kernel<true><<<plan.grid[g], tc2::T2_THREADS, plan.smem[g], stream_>>>(dt, di, (int)plan.items[g].size(), plan.geom[g]);
+        count_launch();
+        stats_.mode_launches += 1;
+        stats_.tc_launches += 1;
+        stats_.tma_launches += 1;
+      }
+      stats_.mode_flops += plan.flops;
+      TNQS_CUDA(cudaGetLastError());
+    }
+    if (tasks.empty()) return rest;
+  } else {
+    tasks = tasks_all;
   }
   struct ImgKey { const void* mat; int KK, MM, last; bool operator<(const ImgKey& o) const {
     return std::tie(mat, KK, MM, last) < std::tie(o.mat, o.KK, o.MM, o.last); } };
@@ -735,15 +792,6 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   for (auto& t : tasks) stats_.gram_bytes += (double)esz_ * 2.0 * t.MM * (double)t.CC;
   // ---- tcgen05 path: ComplexF32, fp32 accumulation (BP messages), one plane, χ ≤ 64 ------------------
   if (c64() && use_tc_ && !acc_double) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<false, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      TNQS_CUDA(cudaFuncSetAttribute(tc::tc_gram_kernel<true, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set = true;
-    }
     std::vector<tc::TcGramTask> tt[2];
     std::vector<int> ids[2];
     size_t smem_max[2] = {0, 0};
@@ -826,14 +874,6 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         done[i] = 1;
       }
       if (grp.empty()) continue;
-      static bool attr_set = false;
-      if (!attr_set) {
-        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        TNQS_CUDA(cudaFuncSetAttribute(gram_dmma_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_set = true;
-      }
       // ~4 CTAs per SM overall, at least 1024 columns per split
       const long long target_cols = std::max<long long>(1024, work / (148 * 4));
       int maxsplit = 1, maxgroups = 1;
@@ -1591,11 +1631,6 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           ct[j].scratch = nullptr;
           jg[j].V = nullptr;
         }
-        static bool attr_set = false;
-        if (!attr_set) {
-          TNQS_CUDA(cudaFuncSetAttribute(chol_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-          attr_set = true;
-        }
         CholTask* dc = upload(ct);
         const size_t sm = (size_t)maxn_g * maxn_g * sizeof(double2) + (size_t)maxn_g * (sizeof(double) + sizeof(int));
         chol_prepare_kernel<<<2 * nm, 256, sm, stream_>>>(dc, 1e-15);
@@ -1668,11 +1703,6 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
             g2[q].A = st[k].theta0; g2[q].B = Vk; g2[q].out = st[k].theta; g2[q].m = rows; g2[q].n = cols;
             jl[q].A = L; jl[q].V = nullptr; jl[q].m = cols; jl[q].n = cols; jl[q].sval = sv1;
             jl[q].perm = (int*)talloc(sizeof(int) * cols);
-          }
-          static bool attr_set2 = false;
-          if (!attr_set2) {
-            TNQS_CUDA(cudaFuncSetAttribute(chol_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-            attr_set2 = true;
           }
           SmallGemmTask* d1 = upload(g1);
           SmallGemmTask* d2 = upload(g2);

@@ -36,7 +36,7 @@ def test_struct_layouts_match_header():
     assert C.sizeof(_lib.ApplyOpts) == 32
     assert C.sizeof(_lib.BpOpts) == 40
     assert C.sizeof(_lib.BpReport) == 16
-    assert C.sizeof(_lib.Stats) == 144
+    assert C.sizeof(_lib.Stats) == 152
 
 
 def test_no_cpu_fallback_without_gpu():

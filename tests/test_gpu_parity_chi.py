@@ -131,11 +131,12 @@ def test_chi32_patch_colour_bp_expect(dtype, tol, null_dirs):
     d_z = float(np.max(np.abs(zs - zo)))
     _report(test="chi32_patch", dtype=np.dtype(dtype).name, null_dirs=null_dirs, truncerr_rel=d_err, sigma_rel=d_sig,
             expect_abs=d_exp, zz_abs=d_zz, bp_message_rel=d_msg, z_after_bp_abs=d_z, max_truncerr=float(np.max(oerrs)),
-            tc_launches=int(st["tc_launches"]), kernel_launches=int(st["kernel_launches"]))
+            tc_launches=int(st["tc_launches"]), tma_launches=int(st["tma_launches"]), kernel_launches=int(st["kernel_launches"]))
     assert d_err <= tol and d_sig <= tol and d_exp <= tol and d_zz <= tol and d_z <= tol
     assert d_msg <= 5 * tol
     if dtype == np.complex64:
         assert st["tc_launches"] > 0  # tcgen05 mode products / final plane-mixing product really ran
+        assert st["tma_launches"] > 0  # … through the TMA-fed warp-specialised kernel (kernels_tc2.cuh)
 
 
 def _hub_graph():
@@ -178,5 +179,6 @@ def test_interior_gate_hub_graph(chi, dtype, tol):
     c2, _ = orc.bp_update(c, seq_idx(g, seq), maxiter=1, tolerance=None)
     d_msg = max(_rel(out2.message(e), c2.msg[(g.index[e[0]], g.index[e[1]])]) for e in seq)
     _report(test="hub_gate", chi=chi, dtype=np.dtype(dtype).name, truncerr_rel=float(d_err), sigma_rel=d_sig, expect_abs=d_exp,
-            zz_abs=float(d_zz), bp_message_rel=d_msg, truncerr=float(oerrs[0]), tc_launches=int(st["tc_launches"]))
+            zz_abs=float(d_zz), bp_message_rel=d_msg, truncerr=float(oerrs[0]), tc_launches=int(st["tc_launches"]),
+            tma_launches=int(st["tma_launches"]))
     assert d_err <= tol and d_sig <= tol and d_exp <= tol and d_zz <= tol and d_msg <= 5 * tol

@@ -643,12 +643,11 @@ std::vector<ModeTask> Engine::launch_mode_tc(std::vector<ModeTask>& tasks_all) {
         tc2::tc2_prep_kernel<<<(unsigned)plan.preps.size(), 256, 0, stream_>>>(dp);
         count_launch();
       }
-      for (int g = 0; g < 2; ++g) {
-        if (plan.tasks[g].empty()) continue;
-        tc2::ModeTask2* dt = upload(plan.tasks[g]);
-        tc2::Item* di = upload(plan.items[g]);
-        if (g == 0) tc2::tc2_mode_kernel<false><<<plan.grid[g], tc2::T2_THREADS, plan.smem[g], stream_>>>(dt, di, (int)plan.items[g].size(), plan.geom[g]);
-        else tc2::tc2_mode_kernel<true><<<plan.grid[g], tc2::T2_THREADS, plan.smem[g], stream_>>>(dt, di, (int)plan.items[g].size(), plan.geom[g]);
+      for (auto& L : plan.launches) {  // one launch per shape class (variant, K chunking, N)
+        tc2::ModeTask2* dt = upload(L.tasks);
+        tc2::Item* di = upload(L.items);
+        if (L.last) tc2::tc2_mode_kernel<true><<<L.grid, tc2::T2_THREADS, L.smem, stream_>>>(dt, di, (int)L.items.size(), L.gm);
+        else tc2::tc2_mode_kernel<false><<<L.grid, tc2::T2_THREADS, L.smem, stream_>>>(dt, di, (int)L.items.size(), L.gm);
         count_launch();
         stats_.mode_launches += 1;
         stats_.tc_launches += 1;

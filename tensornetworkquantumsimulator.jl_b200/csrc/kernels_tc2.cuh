@@ -165,23 +165,30 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // Work item: a strided set of tiles of one task.  The grid is persistent (one CTA per SM); CTA c runs items
 // c, c + gridDim.x, … and every role walks the same list, so the stage / accumulator / image rings keep flowing
 // across item boundaries (the B image of the next item is fetched while the current one is still being multiplied).
-struct Item { int task, tile0, stride, ntile; };
+struct Item { int task, tile0, stride, pad_; };  // tiles tile0 + i·stride, i < Geom::T (tiles past the task's last one are no-ops)
 // launch-wide shared-memory geometry (maxima over the tasks of the launch)
 struct Geom {
   uint32_t slot;   // bytes of one raw (= one lo) ring slot
   uint32_t outb;   // bytes of one output staging buffer (one per epilogue group)
   uint32_t imgb;   // bytes of one B-image buffer
   int nstage, nimg, nbuf, ncol;  // ring depths; accumulator buffers of `ncol` TMEM columns each
+  // shape class of the launch (every task of a launch has the same): the MMA warp then works on kernel parameters and
+  // loop counters only, i.e. on values ptxas keeps in uniform registers — its UTCHMMA operands need no per-lane broadcast
+  int kch, nchunk, NNp;
+  int T;           // tiles per work item
 };
 
-template <bool LAST>
+template <bool LAST, bool INSTR = false>
 __global__ void __launch_bounds__(T2_THREADS, 1)
 tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ items, int nitems, const Geom gm) {
   extern __shared__ __align__(1024) uint8_t smem2[];
   __shared__ __align__(8) uint64_t bar_full[MAX_STAGES], bar_lo[MAX_STAGES], bar_empty[MAX_STAGES];
   __shared__ __align__(8) uint64_t bar_tfull[4], bar_tempty[4], bar_ifull[2], bar_iempty[2];
   __shared__ uint32_t s_tmem;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp-uniform warp index (as CUTLASS' canonical_warp_idx_sync): the role dispatch below is then a uniform branch and the
+  // issue warps' operands can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nstage = gm.nstage, nimg = gm.nimg, nbuf = gm.nbuf;
   uint8_t* const s_stage = smem2;  // [nstage][raw | lo]
   uint8_t* const s_out = s_stage + (size_t)nstage * 2 * gm.slot;
@@ -194,7 +201,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int s = 0; s < nstage; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_lo[s], T2_SPLIT); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < nstage; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_lo[s], T2_SPLIT); mbar_init(&bar_empty[s], 2); }
     for (int b = 0; b < 4; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], 128); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bar_ifull[b], 1); mbar_init(&bar_iempty[b], 2); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -203,8 +210,10 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem = s_tmem;
-  const int dbg = g_tc2_dbg;
-  unsigned long long* const prof = g_tc2_prof ? g_tc2_prof + (size_t)blockIdx.x * 32 : nullptr;
+  // instrumentation (debug switches, per-role cycle counters) exists only in the INSTR instantiation: values loaded from
+  // memory would otherwise make the issue warps' control flow non-uniform in the compiler's eyes
+  const int dbg = INSTR ? g_tc2_dbg : 0;
+  unsigned long long* const prof = (INSTR && g_tc2_prof) ? g_tc2_prof + (size_t)blockIdx.x * 32 : nullptr;
   long long acc[6] = {0, 0, 0, 0, 0, 0};
   const long long tstart = prof ? clock64() : 0;
 
@@ -217,14 +226,14 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
       int ib = 0; uint32_t iph = 0;  // image ring position
       for (int ii = blockIdx.x; ii < nitems; ii += gridDim.x) {
         Item im = items[ii];
-        im.task = bc(im.task); im.tile0 = bc(im.tile0); im.stride = bc(im.stride); im.ntile = bc(im.ntile);
+        im.task = bc(im.task); im.tile0 = bc(im.tile0); im.stride = bc(im.stride);
         const ModeTask2* __restrict__ tp = tasks + im.task;
-        const int kch = bc(tp->kch), nchunk = bc(tp->nchunk), chi_in = bc(tp->chi_in), bpb = LAST ? 4 : bc(tp->bpb);
+        const int kch = gm.kch, nchunk = gm.nchunk, chi_in = bc(tp->chi_in), bpb = LAST ? 4 : bc(tp->bpb);
         const unsigned inner = bcu(tp->inner);
         const uint32_t stg = LAST ? 128u * 128u : (uint32_t)kch * 512u;
         {  // B image of this item, once the MMAs that read the buffer's previous content are done
           { TC2_T0(); mbar_wait(smem_u32(&bar_iempty[ib]), iph ^ 1u); TC2_ACC(0); }
-          const uint32_t img_bytes = (uint32_t)nchunk * 2u * (uint32_t)bc(tp->NNp) * (uint32_t)kch * 4u;
+          const uint32_t img_bytes = (uint32_t)nchunk * 2u * (uint32_t)gm.NNp * (uint32_t)kch * 4u;
           if (lane == 0) mbar_expect_tx(&bar_ifull[ib], img_bytes);
           if (lane == 0)
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -242,7 +251,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         }
         const int kpl = LAST ? 1 : (chi_in >= kch ? 0 : kch / chi_in);  // MID: planes per stage when a stage spans planes
         int tile = im.tile0;
-        for (int ti = 0; ti < im.ntile; ++ti, tile += im.stride) {
+        for (int ti = 0; ti < gm.T; ++ti, tile += im.stride) {
           int p = 0, b0 = 0;  // MID: plane / first row of the stage; LAST: plane / first float
           for (int ch = 0; ch < nchunk; ++ch) {
             { TC2_T0(); mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u); TC2_ACC(2); }
@@ -279,37 +288,42 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
     }
   } else if (warp <= 2) {
     // =============================== MMA issuers (warp 1: even tiles, warp 2: odd tiles) ===============================
-    // Whole warp on warp-uniform values, lane 0 issues.  The shared-memory descriptors of a stage are a base value plus
-    // small constants (the start-address field holds addr >> 4 and never carries: shared memory is < 256 KB), so the loop
-    // body is uniform adds and the MMAs.
+    // One UTCHMMA of this size (M 128, N 2χ', K 8) keeps the tensor pipe busy for 32–64 cycles but takes ~80 cycles to
+    // dispatch from one warp; two issuing warps on alternate tiles (separate TMEM accumulators) overlap their dispatch.
+    // The whole warp runs the loop; lane 0 issues.  Every value below comes from kernel parameters, block / grid indices
+    // and loop counters, so the descriptors sit in uniform registers and consecutive UTCHMMAs are a few instructions apart.
+    // The shared-memory descriptors of a stage are a base value plus small constants (the start-address field holds
+    // addr >> 4 and never carries: shared memory is < 256 KB).
     {
       const int mw = warp - 1;
       int tl = 0;
       int s = 0; uint32_t ph = 0;
       int ib = 0; uint32_t iph = 0;
       int buf = 0; uint32_t bph = 0;  // accumulator ring position
+      const int kch = gm.kch, nchunk = gm.nchunk, NNp = gm.NNp;
+      const uint32_t stg = LAST ? 128u * 128u : (uint32_t)kch * 512u;
       const uint64_t stage_step = (uint64_t)((2u * gm.slot) >> 4);
-      for (int ii = blockIdx.x; ii < nitems; ii += gridDim.x) {
-        Item im = items[ii];
-        im.task = bc(im.task); im.ntile = bc(im.ntile);
-        const ModeTask2* __restrict__ tp = tasks + im.task;
-        const int kch = bc(tp->kch), nchunk = bc(tp->nchunk), NNp = bc(tp->NNp);
-        const uint32_t stg = LAST ? 128u * 128u : (uint32_t)kch * 512u;
+      const uint32_t idesc = make_idesc(128, NNp, LAST ? 0 : 1, 0);
+      const uint32_t per_b = (uint32_t)NNp * (uint32_t)kch * 4u;
+      const uint64_t a_raw0 = LAST ? make_desc(smem_u32(s_stage), 16u, 1024u, 2)                       // K-major SW128: SBO = 8-row group
+                                   : make_desc(smem_u32(s_stage), (uint32_t)kch * 128u, 512u, 1);      // MN-major SW128/32B: LBO = MN-atom stride, SBO = K-atom (4 rows)
+      const uint64_t lo_off = (uint64_t)(stg >> 4);
+      const uint64_t a_k = LAST ? 2u : 64u;                                                             // 32 B / 1024 B per k-step of 8
+      const uint64_t b_img0 = make_desc(smem_u32(s_img), 128u, (uint32_t)kch * 32u, 0);
+      const uint64_t b_lo_off = (uint64_t)(per_b >> 4), chunk_step = (uint64_t)((2u * per_b) >> 4), img_step = (uint64_t)(gm.imgb >> 4);
+      const int nks = kch >> 3;
+      const int n_my = ((int)nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      for (int k = 0; k < n_my; ++k) {
         { TC2_T0(); mbar_wait(smem_u32(&bar_ifull[ib]), iph); TC2_ACC(0); }
-        const uint32_t idesc = make_idesc(128, NNp, LAST ? 0 : 1, 0);
-        const uint32_t per_b = (uint32_t)NNp * (uint32_t)kch * 4u;
-        // descriptors of stage 0 / image chunk 0; stage s adds s·stage_step, chunk c adds c·chunk_step, k-step ks adds ks·a_k / ks·16
-        const uint64_t a_raw0 = LAST ? make_desc(smem_u32(s_stage), 16u, 1024u, 2)                       // K-major SW128: SBO = 8-row group
-                                     : make_desc(smem_u32(s_stage), (uint32_t)kch * 128u, 512u, 1);      // MN-major SW128/32B: LBO = MN-atom stride, SBO = K-atom (4 rows)
-        const uint64_t lo_off = (uint64_t)(stg >> 4);
-        const uint64_t a_k = LAST ? 2u : 64u;                                                             // 32 B / 1024 B per k-step of 8
-        const uint64_t b_hi0 = make_desc(smem_u32(s_img + (size_t)ib * gm.imgb), 128u, (uint32_t)kch * 32u, 0);
-        const uint64_t b_lo_off = (uint64_t)(per_b >> 4), chunk_step = (uint64_t)((2u * per_b) >> 4);
-        const int nks = kch >> 3;
-        for (int ti = 0; ti < im.ntile; ++ti, ++tl) {
-          if ((tl & 1) != mw) {  // the other issuer's tile: follow its stages (a parity wait must never fall a phase behind)
+        const uint64_t b_hi0 = b_img0 + (uint64_t)ib * img_step;
+        for (int ti = 0; ti < gm.T; ++ti, ++tl) {
+          if ((tl & 1) != mw) {
+            // The other issuer's tile: observe every phase of its stages (a parity wait must never fall a phase behind) and
+            // take part in releasing them (empty[] counts both issuers), so a stage cannot be refilled before this warp has
+            // seen it — the protocol does not depend on how far one warp runs ahead of the other.
             for (int ch = 0; ch < nchunk; ++ch) {
               mbar_wait(smem_u32(&bar_full[s]), ph);
+              if (lane == 0) mbar_arrive(&bar_empty[s]);
               if (++s == nstage) { s = 0; ph ^= 1u; }
             }
             if (++buf == nbuf) { buf = 0; bph ^= 1u; }
@@ -351,17 +365,16 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         if (lane == 0) umma_commit(&bar_iempty[ib]);  // the image buffer is free once every MMA of the item has read it
         if (++ib == nimg) { ib = 0; iph ^= 1u; }
       }
-      if (prof && mw == 0 && lane == 0) { prof[8] = acc[0]; prof[9] = acc[1]; prof[10] = acc[2]; prof[11] = acc[3]; prof[12] = acc[4]; prof[13] = clock64() - tstart; }
+      if (prof && lane == 0 && mw == 0) { prof[8] = acc[0]; prof[9] = acc[1]; prof[10] = acc[2]; prof[11] = acc[3]; prof[12] = acc[4]; prof[13] = clock64() - tstart; }
     }
   } else if (warp < 11) {
     // =============================== splitters: lo = rna(x − trunc(x)) ===============================
     const int t = tid - 96;
     int s = 0; uint32_t ph = 0;
-    for (int ii = blockIdx.x; ii < nitems; ii += gridDim.x) {
-      const Item im = items[ii];
-      const ModeTask2* __restrict__ tp = tasks + im.task;
-      const int nchunks = im.ntile * tp->nchunk;
-      const int n16 = LAST ? 1024 : tp->kch * 32;  // 16-byte pieces of a stage
+    {
+      const int n_my = ((int)nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int nchunks = n_my * gm.T * gm.nchunk;
+      const int n16 = LAST ? 1024 : gm.kch * 32;  // 16-byte pieces of a stage
       for (int c = 0; c < nchunks; ++c) {
         { TC2_T0(); mbar_wait(smem_u32(&bar_full[s]), ph); TC2_ACC(0); }
         const long long tw_ = prof ? clock64() : 0;
@@ -399,9 +412,9 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
     int buf = 0; uint32_t bph = 0;  // accumulator ring position (advanced for every tile, both groups)
     for (int ii = blockIdx.x; ii < nitems; ii += gridDim.x) {
       Item im = items[ii];
-      im.task = bc(im.task); im.tile0 = bc(im.tile0); im.stride = bc(im.stride); im.ntile = bc(im.ntile);
+      im.task = bc(im.task); im.tile0 = bc(im.tile0); im.stride = bc(im.stride);
       const ModeTask2* __restrict__ tp = tasks + im.task;
-      const int NNp = bc(tp->NNp);
+      const int NNp = gm.NNp;
       const unsigned inner = bcu(tp->inner), CC = bcu(tp->CC);
       const int npl = bc(tp->npl_out), pp0 = bc(tp->pp0), nc = bc(tp->nc), c0 = bc(tp->c0), bpb = LAST ? 4 : bc(tp->bpb);
       if (e == 0) tmap_acquire(&tp->out_map);
@@ -413,7 +426,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         d_o = step / inner; d_n = step - d_o * inner;
       }
       int tile = im.tile0;
-      for (int ti = 0; ti < im.ntile; ++ti, ++tl, tile += im.stride) {
+      for (int ti = 0; ti < gm.T; ++ti, ++tl, tile += im.stride) {
         const int mybuf = buf;
         const uint32_t myph = bph;
         const unsigned to = o, tn = n;
@@ -450,12 +463,13 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
           auto emit = [&](const uint32_t (&v)[16], int g) {
             if (!LAST) {
               // D[(col,ri), (j',part)] → re = D[(c,0),(j',0)] − D[(c,1),(j',1)], im = D[(c,1),(j',0)] + D[(c,0),(j',1)]
+              float other[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) other[q] = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * q + 1]), 1);  // all shuffles in flight first
 #pragma unroll
               for (int q = 0; q < 8; ++q) {
-                const float own = __uint_as_float(v[2 * q]);
-                const float other = __shfl_xor_sync(0xffffffffu, __uint_as_float(v[2 * q + 1]), 1);
                 const int jl = g * 8 + q;  // local output index = plane · nc + row
-                if (jl < nrows) dstm[(jl < nc ? jl : jl + 3 * nc) * 32] = own + sgn * other;
+                if (jl < nrows) dstm[(jl < nc ? jl : jl + 3 * nc) * 32] = fmaf(sgn, other[q], __uint_as_float(v[2 * q]));
               }
             } else {
               // D[col, (j',ri')] is the output row as stored
@@ -475,6 +489,10 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             ld_tmem16(trow + (uint32_t)g0 * 16u, va);
             ld_tmem16(trow + (uint32_t)g0 * 16u + 16u, vb);
             tmem_ld_wait();
+            if (g0 + 2 >= ng) {  // the accumulator is in registers: hand the TMEM buffer back before the shuffles / stores
+              asm volatile("tcgen05.fence::before_thread_sync;");
+              mbar_arrive(&bar_tempty[mybuf]);
+            }
             staging_free();
             emit(va, g0); emit(vb, g0 + 1);
           }
@@ -482,12 +500,18 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             uint32_t va[16];
             ld_tmem16(trow + (uint32_t)g0 * 16u, va);
             tmem_ld_wait();
+            if (g0 + 1 >= ng) {
+              asm volatile("tcgen05.fence::before_thread_sync;");
+              mbar_arrive(&bar_tempty[mybuf]);
+            }
             staging_free();
             emit(va, g0);
           }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        mbar_arrive(&bar_tempty[mybuf]);  // the accumulator buffer may be overwritten
+        if (dbg & 4) {
+          asm volatile("tcgen05.fence::before_thread_sync;");
+          mbar_arrive(&bar_tempty[mybuf]);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, 128;" ::"r"(bar_a) : "memory");
         const long long tst_ = prof ? clock64() : 0;
@@ -669,17 +693,21 @@ inline bool build_task(const ModeShape& t, const Window& w, int kch, ModeTask2& 
   return true;
 }
 
-// A batch of mode products cut into tasks for the two kernel variants (index 0: MID, 1: LAST), the B images they
-// need (one per distinct (matrix, window)) and the CTA → task table of each launch.
+// A batch of mode products cut into tasks, grouped into launches by shape class (variant, kch, nchunk, NNp), with the B
+// images they need (one per distinct (matrix, window)) and the work items of each launch.
+struct Launch {
+  bool last = false;
+  Geom gm{};
+  std::vector<ModeTask2> tasks;
+  std::vector<Item> items;
+  int grid = 0;
+  size_t smem = 0;
+};
 struct Plan {
-  std::vector<ModeTask2> tasks[2];
-  std::vector<Item> items[2];
-  Geom geom[2];
-  int grid[2] = {0, 0};
+  std::vector<Launch> launches;
   std::vector<PrepTask2> preps;
-  size_t smem[2] = {0, 0};
   double flops = 0;
-  bool empty() const { return tasks[0].empty() && tasks[1].empty(); }
+  bool empty() const { return launches.empty(); }
 };
 struct ImageKey {
   const void* mat; int KK, MM, last, pp0, npl, c0, nc, kch;
@@ -698,7 +726,6 @@ inline bool plan_add(Plan& pl, const ModeShape& t, Alloc&& alloc_image, Cache& i
   std::vector<Window> win;
   if (!plan_windows(t, &kch, win)) return false;
   const bool last = t.inner == 1;
-  const int g = last ? 1 : 0;
   std::vector<ModeTask2> mine;
   std::vector<PrepTask2> preps;
   std::vector<std::pair<ImageKey, float*>> fresh;
@@ -725,8 +752,23 @@ inline bool plan_add(Plan& pl, const ModeShape& t, Alloc&& alloc_image, Cache& i
   }
   for (auto& fr : fresh) images[fr.first] = fr.second;
   for (auto& p : preps) pl.preps.push_back(p);
-  mine[0].nsib = (int)mine.size();
-  for (auto& k : mine) pl.tasks[g].push_back(k);
+  // windows of one product may fall into different shape classes (a narrower last window): siblings are the runs of
+  // consecutive windows of the same class
+  for (size_t i = 0; i < mine.size();) {
+    size_t j = i;
+    while (j < mine.size() && mine[j].NNp == mine[i].NNp && mine[j].nchunk == mine[i].nchunk) ++j;
+    Launch* L = nullptr;
+    for (auto& c : pl.launches)
+      if (c.last == last && c.gm.kch == kch && c.gm.nchunk == mine[i].nchunk && c.gm.NNp == mine[i].NNp) L = &c;
+    if (!L) {
+      pl.launches.emplace_back();
+      L = &pl.launches.back();
+      L->last = last; L->gm.kch = kch; L->gm.nchunk = mine[i].nchunk; L->gm.NNp = mine[i].NNp;
+    }
+    mine[i].nsib = (int)(j - i);
+    for (size_t q = i; q < j; ++q) L->tasks.push_back(mine[q]);
+    i = j;
+  }
   pl.flops += 8.0 * t.KK * t.MM * (double)t.CC;
   return true;
 }
@@ -734,21 +776,15 @@ inline bool plan_add(Plan& pl, const ModeShape& t, Alloc&& alloc_image, Cache& i
 // (and of the sibling windows of one product) are adjacent in the list, so that the CTAs running at the same time stream
 // neighbouring pieces of the same tensor rows (same DRAM pages; the second read of a shared input tile hits L2).
 inline bool plan_finish(Plan& pl, int sms = 148) {
-  for (int g = 0; g < 2; ++g) {
-    pl.items[g].clear();
-    pl.grid[g] = 0;
-    pl.smem[g] = 0;
-    if (pl.tasks[g].empty()) continue;
-    const bool last = g == 1;
-    Geom gm{};
+  for (auto& L : pl.launches) {
+    Geom& gm = L.gm;
+    const bool last = L.last;
     long long total = 0;
-    for (auto& k : pl.tasks[g]) {
-      total += k.ntiles;
-      gm.slot = std::max<uint32_t>(gm.slot, last ? 16384u : (uint32_t)k.kch * 512u);
-      gm.outb = std::max<uint32_t>(gm.outb, last ? (uint32_t)k.NNp * 512u : (uint32_t)k.NNp * 256u);
-      gm.imgb = std::max<uint32_t>(gm.imgb, (uint32_t)k.nchunk * 2u * (uint32_t)k.NNp * (uint32_t)k.kch * 4u);
-      gm.ncol = std::max(gm.ncol, k.NNp);
-    }
+    for (auto& k : L.tasks) total += k.ntiles;
+    gm.slot = last ? 16384u : (uint32_t)gm.kch * 512u;
+    gm.outb = last ? (uint32_t)gm.NNp * 512u : (uint32_t)gm.NNp * 256u;
+    gm.imgb = (uint32_t)gm.nchunk * 2u * (uint32_t)gm.NNp * (uint32_t)gm.kch * 4u;
+    gm.ncol = gm.NNp;
     gm.outb = (gm.outb + 1023u) & ~1023u;
     gm.imgb = (gm.imgb + 1023u) & ~1023u;
     gm.nbuf = 4 * gm.ncol <= 512 ? 4 : 2;
@@ -757,18 +793,20 @@ inline bool plan_finish(Plan& pl, int sms = 148) {
     if (ns < 3) { gm.nimg = 1; ns = ((long long)SMEM_BUDGET - 2ll * gm.outb - (long long)gm.imgb) / (2ll * gm.slot); }
     if (ns < 2) return false;
     gm.nstage = (int)std::min<long long>(MAX_STAGES, ns);
-    pl.geom[g] = gm;
-    pl.smem[g] = (size_t)gm.nstage * 2 * gm.slot + 2 * (size_t)gm.outb + (size_t)gm.nimg * gm.imgb;
+    L.smem = (size_t)gm.nstage * 2 * gm.slot + 2 * (size_t)gm.outb + (size_t)gm.nimg * gm.imgb;
+    // every item has exactly T tiles (those past a task's last tile are no-ops): ~24 items per SM, 4 ≤ T ≤ 64
     const int T = (int)std::max<long long>(4, std::min<long long>(64, total / ((long long)sms * 24)));
-    for (size_t i = 0; i < pl.tasks[g].size();) {
-      const int nsib = std::max(1, pl.tasks[g][i].nsib);
-      const int ntiles = pl.tasks[g][i].ntiles;
+    gm.T = T;
+    L.items.clear();
+    for (size_t i = 0; i < L.tasks.size();) {
+      const int nsib = std::max(1, L.tasks[i].nsib);
+      const int ntiles = L.tasks[i].ntiles;
       const int nit = std::max(1, (ntiles + T - 1) / T);
       for (int j = 0; j < nit; ++j)
-        for (int w = 0; w < nsib; ++w) pl.items[g].push_back({(int)i + w, j, nit, (ntiles - j + nit - 1) / nit});
+        for (int w = 0; w < nsib; ++w) L.items.push_back({(int)i + w, j, nit, 0});
       i += nsib;
     }
-    pl.grid[g] = (int)std::min<size_t>((size_t)sms, pl.items[g].size());
+    L.grid = (int)std::min<size_t>((size_t)sms, L.items.size());
   }
   return true;
 }

@@ -21,6 +21,7 @@ using namespace tnqs;
 struct Case { const char* name; int P_in, P_out; unsigned outer; int chi_in, chi_out; unsigned inner; };
 
 static int g_stage_override = 0;
+static bool g_instr = false;  // run the instrumented instantiation (debug switches / role counters)
 
 // runs `batch` independent copies of the product (distinct tensors, same matrix); returns max error / rms over samples
 static bool run_case(const Case& c, int batch, bool timing) {
@@ -55,30 +56,37 @@ static bool run_case(const Case& c, int batch, bool timing) {
   if (!ok) { printf("%-34s : NOT ELIGIBLE for the TMA path\n", c.name); return false; }
   if (!tc2::plan_finish(plan)) { printf("%-34s : plan_finish failed\n", c.name); return false; }
   if (g_stage_override > 0)
-    for (int g = 0; g < 2; ++g) plan.geom[g].nstage = std::min(plan.geom[g].nstage, g_stage_override);
+    for (auto& L : plan.launches) L.gm.nstage = std::min(L.gm.nstage, g_stage_override);
   tc2::PrepTask2* dprep;
   CK(cudaMalloc(&dprep, plan.preps.size() * sizeof(tc2::PrepTask2)));
   CK(cudaMemcpy(dprep, plan.preps.data(), plan.preps.size() * sizeof(tc2::PrepTask2), cudaMemcpyHostToDevice));
   tc2::tc2_prep_kernel<<<(unsigned)plan.preps.size(), 256>>>(dprep);
   CK(cudaGetLastError());
-  tc2::ModeTask2* dt[2] = {nullptr, nullptr};
-  tc2::Item* dc[2] = {nullptr, nullptr};
-  for (int g = 0; g < 2; ++g) {
-    if (plan.tasks[g].empty()) continue;
-    CK(cudaMalloc(&dt[g], plan.tasks[g].size() * sizeof(tc2::ModeTask2)));
-    CK(cudaMemcpy(dt[g], plan.tasks[g].data(), plan.tasks[g].size() * sizeof(tc2::ModeTask2), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&dc[g], plan.items[g].size() * sizeof(tc2::Item)));
-    CK(cudaMemcpy(dc[g], plan.items[g].data(), plan.items[g].size() * sizeof(tc2::Item), cudaMemcpyHostToDevice));
+  std::vector<tc2::ModeTask2*> dt(plan.launches.size(), nullptr);
+  std::vector<tc2::Item*> dc(plan.launches.size(), nullptr);
+  for (size_t g = 0; g < plan.launches.size(); ++g) {
+    auto& L = plan.launches[g];
+    CK(cudaMalloc(&dt[g], L.tasks.size() * sizeof(tc2::ModeTask2)));
+    CK(cudaMemcpy(dt[g], L.tasks.data(), L.tasks.size() * sizeof(tc2::ModeTask2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&dc[g], L.items.size() * sizeof(tc2::Item)));
+    CK(cudaMemcpy(dc[g], L.items.data(), L.items.size() * sizeof(tc2::Item), cudaMemcpyHostToDevice));
   }
   auto launch = [&] {
-    if (!plan.tasks[0].empty()) tc2::tc2_mode_kernel<false><<<plan.grid[0], tc2::T2_THREADS, plan.smem[0]>>>(dt[0], dc[0], (int)plan.items[0].size(), plan.geom[0]);
-    if (!plan.tasks[1].empty()) tc2::tc2_mode_kernel<true><<<plan.grid[1], tc2::T2_THREADS, plan.smem[1]>>>(dt[1], dc[1], (int)plan.items[1].size(), plan.geom[1]);
+    for (size_t g = 0; g < plan.launches.size(); ++g) {
+      auto& L = plan.launches[g];
+      if (g_instr) {
+        if (L.last) tc2::tc2_mode_kernel<true, true><<<L.grid, tc2::T2_THREADS, L.smem>>>(dt[g], dc[g], (int)L.items.size(), L.gm);
+        else tc2::tc2_mode_kernel<false, true><<<L.grid, tc2::T2_THREADS, L.smem>>>(dt[g], dc[g], (int)L.items.size(), L.gm);
+      } else {
+        if (L.last) tc2::tc2_mode_kernel<true><<<L.grid, tc2::T2_THREADS, L.smem>>>(dt[g], dc[g], (int)L.items.size(), L.gm);
+        else tc2::tc2_mode_kernel<false><<<L.grid, tc2::T2_THREADS, L.smem>>>(dt[g], dc[g], (int)L.items.size(), L.gm);
+      }
+    }
   };
   launch();
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-34s : KERNEL ERROR %s\n", c.name, cudaGetErrorString(e)); exit(3); }
-  const int g0 = plan.tasks[0].empty() ? 1 : 0;
-  const tc2::ModeTask2& k0 = plan.tasks[g0][0];
+  const tc2::Launch& L0 = plan.launches[0];
   // verification: all outputs of copy 0 when small, a random sample otherwise; the last copy is compared with copy 0
   std::vector<float2> hout((size_t)out_n), hlast((size_t)out_n);
   CK(cudaMemcpy(hout.data(), dout, (size_t)out_n * 8, cudaMemcpyDeviceToHost));
@@ -114,10 +122,12 @@ static bool run_case(const Case& c, int batch, bool timing) {
     if (std::isnan(hout[(size_t)i].x)) ++nan_count;
   const double rms = std::sqrt(sumsq / std::max<long long>(1, nsamp));
   const bool pass = nan_count == 0 && diff_last == 0 && maxerr / rms < 2e-5;
-  const tc2::Geom& gm = plan.geom[g0];
-  printf("%-34s : %s  max|err|/rms = %.2e  unwritten = %lld  copy-mismatch = %lld  [tasks %zu+%zu items %zu+%zu grid %d kch %d NNp %d nstage %d nimg %d nbuf %d smem %zu]\n",
-         c.name, pass ? "ok  " : "FAIL", maxerr / rms, nan_count, diff_last, plan.tasks[0].size(), plan.tasks[1].size(), plan.items[0].size(),
-         plan.items[1].size(), plan.grid[g0], k0.kch, k0.NNp, gm.nstage, gm.nimg, gm.nbuf, std::max(plan.smem[0], plan.smem[1]));
+  const tc2::Geom& gm = L0.gm;
+  size_t ntask = 0, nitem = 0;
+  for (auto& L : plan.launches) { ntask += L.tasks.size(); nitem += L.items.size(); }
+  printf("%-34s : %s  max|err|/rms = %.2e  unwritten = %lld  copy-mismatch = %lld  [%zu launch(es) %s tasks %zu items %zu grid %d T %d kch %d nchunk %d NNp %d nstage %d nimg %d nbuf %d smem %zu]\n",
+         c.name, pass ? "ok  " : "FAIL", maxerr / rms, nan_count, diff_last, plan.launches.size(), L0.last ? "LAST" : "MID", ntask, nitem, L0.grid, gm.T,
+         gm.kch, gm.nchunk, gm.NNp, gm.nstage, gm.nimg, gm.nbuf, L0.smem);
   if (timing) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -134,7 +144,7 @@ static bool run_case(const Case& c, int batch, bool timing) {
   }
   for (void* p : imgs) cudaFree(p);
   cudaFree(dprep);
-  for (int g = 0; g < 2; ++g) { if (dt[g]) cudaFree(dt[g]); if (dc[g]) cudaFree(dc[g]); }
+  for (size_t g = 0; g < dt.size(); ++g) { cudaFree(dt[g]); cudaFree(dc[g]); }
   cudaFree(din); cudaFree(dout); cudaFree(dmat);
   return pass;
 }
@@ -144,6 +154,9 @@ int main(int argc, char** argv) {
   if (argc > 2) g_stage_override = atoi(argv[2]);
   CK(cudaFuncSetAttribute(tc2::tc2_mode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
   CK(cudaFuncSetAttribute(tc2::tc2_mode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+  CK(cudaFuncSetAttribute((tc2::tc2_mode_kernel<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+  CK(cudaFuncSetAttribute((tc2::tc2_mode_kernel<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 225 * 1024));
+  g_instr = argc > 1 && (!strcmp(argv[1], "roles") || !strcmp(argv[1], "decomp"));
   const Case cases[] = {
       {"MID chi32 leg2 (inner 32)", 1, 1, 2 * 32 * 32, 32, 32, 32},
       {"MID chi32 leg1 (inner 1024)", 1, 1, 2 * 32, 32, 32, 1024},

@@ -53,6 +53,13 @@ typedef struct {
   double  cutoff;            /* <0: none; relative cutoff on σ² (NDTensors truncate!)            */
   int32_t normalize_tensors; /* default 1 (simple_update.jl:23)                                  */
   double  sqrt_cutoff;       /* <0: default 10*eps(real(T)) (simple_update.jl:32-33)             */
+  /* the remaining factorize_svd keywords that simple_update forwards (simple_update.jl:53-59) */
+  int32_t use_absolute_cutoff; /* default 0: 1 = drop while σ² ≤ cutoff, truncerr unscaled (NDTensors truncate!) */
+  int32_t use_relative_cutoff; /* default 1: cutoff is relative to Σσ²; 0 = relative to 1              */
+  int32_t svd_alg;           /* 0 "divide_and_conquer" (default), 1 "qr_iteration", 2 "recursive": LAPACK driver
+                                names of the reference; this library always runs its Jacobi SVD, whose singular
+                                values and truncation errors agree with either driver to round-off          */
+  int32_t reserved;
 } tnqs_apply_opts;
 
 /* keyword arguments of update(bpc; …)  (src/MessagePassing/beliefpropagationcache.jl:56-72,103-119) */

@@ -228,19 +228,31 @@ def pseudo_sqrt_inv_sqrt(m: np.ndarray, cutoff: float) -> Tuple[np.ndarray, np.n
 
 
 def truncate_spectrum(p: np.ndarray, maxdim: Optional[int], cutoff: Optional[float],
-                      mindim: int = 1) -> Tuple[int, float]:
-    """NDTensors `truncate!` on P = σ² sorted descending (called through
-    `factorize_svd`, simple_update.jl:53-59): drop from the tail while n > maxdim, then with the
-    default relative cutoff keep dropping while (discarded + P[n]) ≤ cutoff·ΣP and n > mindim.
-    Returns (kept n, truncerr = discarded/ΣP)."""
+                      mindim: int = 1, use_absolute_cutoff: bool = False,
+                      use_relative_cutoff: bool = True) -> Tuple[int, float]:
+    """NDTensors `truncate!` on P = σ² sorted descending (called through `factorize_svd`,
+    simple_update.jl:53-59; NDTensors is not vendored — behaviour as summarised in SURVEY.md §8a): drop
+    from the tail while n > maxdim (whatever mindim says); then, while n > mindim, either the absolute
+    test P[n] ≤ cutoff (truncerr left unscaled) or the summed test (discarded + P[n]) ≤ cutoff·scale with
+    scale = ΣP when `use_relative_cutoff` (else 1) and truncerr /= scale.  A single candidate is never
+    truncated.  Returns (kept n, truncerr)."""
     n = len(p)
+    if n <= 1:
+        return n, 0.0
     total = float(np.sum(p))
-    scale = total if total > 0 else 1.0
     disc = 0.0
+    mindim = max(1, int(mindim))
     if maxdim is not None:
-        while n > max(maxdim, mindim) and n > 0:
+        while n > max(int(maxdim), 1):
             disc += float(p[n - 1])
             n -= 1
+    if use_absolute_cutoff:
+        if cutoff is not None:
+            while n > mindim and float(p[n - 1]) <= cutoff:
+                disc += float(p[n - 1])
+                n -= 1
+        return n, disc
+    scale = (total if total > 0 else 1.0) if use_relative_cutoff else 1.0
     if cutoff is not None:
         while n > mindim and (disc + float(p[n - 1])) <= cutoff * scale:
             disc += float(p[n - 1])
@@ -251,7 +263,7 @@ def truncate_spectrum(p: np.ndarray, maxdim: Optional[int], cutoff: Optional[flo
 def simple_update_two_site(gate: np.ndarray, t1: np.ndarray, t2: np.ndarray, ax1: int, ax2: int,
                            envs1: Dict[int, np.ndarray], envs2: Dict[int, np.ndarray],
                            maxdim=None, cutoff=None, normalize_tensors=True, sqrt_cutoff=None,
-                           mindim=1):
+                           mindim=1, use_absolute_cutoff=False, use_relative_cutoff=True, alg="divide_and_conquer"):
     """Two-site branch of `simple_update` (simple_update.jl:29-68).  `t1`,`t2` are the site
     tensors (d, legs…); `ax1`/`ax2` the axis of the shared bond in each; `envs_i` maps the axis of
     every *other* bond leg of site i to its incoming message.  `gate` is the d²×d² matrix in
@@ -284,12 +296,18 @@ def simple_update_two_site(gate: np.ndarray, t1: np.ndarray, t2: np.ndarray, ax1
     theta = np.einsum("xyst,asct->axcy", g4, theta)
     n1, n2 = r1.shape[0], r2.shape[0]
     mat = theta.reshape(n1 * d1, n2 * d2)
-    try:
-        u, s, vh = np.linalg.svd(mat, full_matrices=False)  # gesdd  :53-59
-    except np.linalg.LinAlgError:  # NDTensors falls back to qr_iteration
+    if alg == "qr_iteration":  # `alg` of factorize_svd: LAPACK gesvd
         import scipy.linalg
         u, s, vh = scipy.linalg.svd(mat, full_matrices=False, lapack_driver="gesvd")
-    keep, err = truncate_spectrum((s.astype(np.float64)) ** 2, maxdim, cutoff, mindim)
+    elif alg in ("divide_and_conquer", "recursive"):
+        try:
+            u, s, vh = np.linalg.svd(mat, full_matrices=False)  # gesdd  :53-59
+        except np.linalg.LinAlgError:  # NDTensors falls back to qr_iteration
+            import scipy.linalg
+            u, s, vh = scipy.linalg.svd(mat, full_matrices=False, lapack_driver="gesvd")
+    else:
+        raise ValueError(f"unknown SVD algorithm {alg!r}")
+    keep, err = truncate_spectrum((s.astype(np.float64)) ** 2, maxdim, cutoff, mindim, use_absolute_cutoff, use_relative_cutoff)
     u, s, vh = u[:, :keep], s[:keep], vh[:keep, :]
     rs_ = np.sqrt(s).astype(s.dtype)
     f1 = (u * rs_).reshape(n1, d1, keep)                      # U√S      [r1,s1,c]
@@ -316,7 +334,8 @@ def simple_update_two_site(gate: np.ndarray, t1: np.ndarray, t2: np.ndarray, ax1
 
 
 def apply_gate(c: OracleCache, gate: np.ndarray, verts: Sequence[int], maxdim=None, cutoff=None,
-               normalize_tensors=True, sqrt_cutoff=None, mindim=1) -> float:
+               normalize_tensors=True, sqrt_cutoff=None, mindim=1, use_absolute_cutoff=False,
+               use_relative_cutoff=True, alg="divide_and_conquer") -> float:
     """`apply_gate!` (src/Apply/apply_gates.jl:101-143), in place on `c`; returns truncerr."""
     nvs = len(verts)
     if not 1 <= nvs <= 2:
@@ -337,7 +356,8 @@ def apply_gate(c: OracleCache, gate: np.ndarray, verts: Sequence[int], maxdim=No
     envs1 = {c.leg(v1, w): c.message(w, v1) for _, w in c.incident[v1] if w != v2}  # :122
     envs2 = {c.leg(v2, w): c.message(w, v2) for _, w in c.incident[v2] if w != v1}
     t1, t2, s, err = simple_update_two_site(gate, c.T[v1], c.T[v2], ax1, ax2, envs1, envs2,
-                                            maxdim, cutoff, normalize_tensors, sqrt_cutoff, mindim)
+                                            maxdim, cutoff, normalize_tensors, sqrt_cutoff, mindim,
+                                            use_absolute_cutoff, use_relative_cutoff, alg)
     m = np.diag(s).astype(c.dtype)  # :126-136, σ ≥ 0 so the sign fix is the identity
     c.msg[(v1, v2)] = m.copy()
     c.msg[(v2, v1)] = m.copy()

@@ -14,7 +14,9 @@ ERRORS = {1: "EINVAL", 2: "ENOTADJ", 3: "ENSITES", 4: "ECUDA", 5: "EDOMAIN", 6: 
 
 class ApplyOpts(C.Structure):
     _fields_ = [("maxdim", C.c_int32), ("mindim", C.c_int32), ("cutoff", C.c_double),
-                ("normalize_tensors", C.c_int32), ("sqrt_cutoff", C.c_double)]
+                ("normalize_tensors", C.c_int32), ("sqrt_cutoff", C.c_double),
+                ("use_absolute_cutoff", C.c_int32), ("use_relative_cutoff", C.c_int32), ("svd_alg", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class BpOpts(C.Structure):

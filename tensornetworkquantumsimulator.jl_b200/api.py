@@ -262,9 +262,15 @@ class BeliefPropagationCache:
 # kwargs → C structs
 # ---------------------------------------------------------------------------------------------
 
+_SVD_ALGS = {"divide_and_conquer": 0, "qr_iteration": 1, "recursive": 2}
+
+
 def _apply_opts(kw: Optional[dict]) -> _lib.ApplyOpts:
+    """`apply_kwargs` of `apply_gates` → C struct: `maxdim`, `cutoff`, `normalize_tensors`, `sqrt_cutoff`
+    (`simple_update.jl:21-33`) and what `factorize_svd` takes (`simple_update.jl:53-59`): `mindim`,
+    `use_absolute_cutoff`, `use_relative_cutoff`, `alg`."""
     kw = dict(kw or {})
-    o = _lib.ApplyOpts(0, 1, -1.0, 1, -1.0)
+    o = _lib.ApplyOpts(0, 1, -1.0, 1, -1.0, 0, 1, 0, 0)
     for k, v in kw.items():
         if k == "maxdim":
             o.maxdim = int(v) if v is not None else 0
@@ -276,9 +282,17 @@ def _apply_opts(kw: Optional[dict]) -> _lib.ApplyOpts:
             o.normalize_tensors = int(bool(v))
         elif k == "sqrt_cutoff":
             o.sqrt_cutoff = float(v) if v is not None else -1.0
+        elif k == "use_absolute_cutoff":
+            o.use_absolute_cutoff = int(bool(v))
+        elif k == "use_relative_cutoff":
+            o.use_relative_cutoff = int(bool(v))
+        elif k == "alg":
+            if v not in _SVD_ALGS:
+                raise ArgumentError(f"unknown SVD algorithm {v!r} (supported: {sorted(_SVD_ALGS)})")
+            o.svd_alg = _SVD_ALGS[v]
         else:
-            raise ArgumentError(f"unsupported apply keyword {k!r} (supported: maxdim, mindim, cutoff, "
-                                "normalize_tensors, sqrt_cutoff)")
+            raise ArgumentError(f"unsupported apply keyword {k!r} (supported: maxdim, mindim, cutoff, normalize_tensors, "
+                                "sqrt_cutoff, use_absolute_cutoff, use_relative_cutoff, alg)")
     return o
 
 

@@ -192,6 +192,8 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   msg_dim_.assign(2 * ne, 0);
   msg_next_dim_.assign(2 * ne, 0);
   msg_set_.assign(2 * ne, 0);
+  d_errflags_ = (double*)dalloc(2 * sizeof(double));
+  TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -230,6 +232,8 @@ Engine::Engine(const Engine& o)
     msg_[de] = dalloc(b);
     TNQS_CUDA(cudaMemcpyAsync(msg_[de], o.msg_[de], b, cudaMemcpyDeviceToDevice, stream_));
   }
+  d_errflags_ = (double*)dalloc(2 * sizeof(double));
+  TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -248,6 +252,7 @@ Engine::~Engine() {
   for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
+  if (d_errflags_) cudaFreeAsync(d_errflags_, stream_);
   if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
   if (ev0_) cudaEventDestroy(ev0_);
   if (ev1_) cudaEventDestroy(ev1_);
@@ -973,7 +978,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
 
 template <int LPP, int RPL, int MAXT, int MINB>
 static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntasks, int BC, int C, int ld, size_t smem,
-                                  double dead_rel2, cudaStream_t s) {
+                                  double dead_rel2, double* nonconv, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -989,7 +994,7 @@ static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntask
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   SlowLog sl("cudaLaunchKernelEx(jacobi)");
-  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2));
+  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2, nonconv));
 }
 
 void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
@@ -1037,9 +1042,9 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
     TNQS_CUDA(cudaMemsetAsync(aux, 0, sizeof(JacobiAux) * nb, stream_));
     // register budget: MINB CTAs of MAXT threads per SM
     const int thr = std::max(32, BC * LPP);
-#define TNQS_JAC(L, R) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
-    else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); \
-    else launch_jacobi_cluster<L, R, 512, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, stream_); } while (0)
+#define TNQS_JAC(L, R) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
+    else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
+    else launch_jacobi_cluster<L, R, 512, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); } while (0)
     bool launched = true;
     try {
       if (LPP == 16) {
@@ -1078,11 +1083,11 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
   const int pairs = (maxn + 1) / 2;
   const int maxwarps = maxm <= 128 ? 32 : (maxm <= 256 ? 16 : 8);  // register budget per lane grows with m
   const int warps = std::max(1, std::min(maxwarps, pairs));
-  if (maxm <= 32) jacobi_kernel<1><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
-  else if (maxm <= 64) jacobi_kernel<2><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
-  else if (maxm <= 128) jacobi_kernel<4><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
-  else if (maxm <= 256) jacobi_kernel<8><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
-  else if (maxm <= 512) jacobi_kernel<16><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16);
+  if (maxm <= 32) jacobi_kernel<1><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16, d_errflags_);
+  else if (maxm <= 64) jacobi_kernel<2><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16, d_errflags_);
+  else if (maxm <= 128) jacobi_kernel<4><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16, d_errflags_);
+  else if (maxm <= 256) jacobi_kernel<8><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16, d_errflags_);
+  else if (maxm <= 512) jacobi_kernel<16><<<nb, warps * 32, 0, stream_>>>(d, 40, 8.9e-16, d_errflags_);
   else throw Error(TNQS_EINVAL, "matrix too large for the batched Jacobi kernel (max 512 rows)");
   count_launch();
   TNQS_CUDA(cudaGetLastError());
@@ -1482,6 +1487,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           t.proj = talloc((size_t)chi * chi * esz_);
           t.chi = chi;
           t.flags = nullptr;
+          t.errflags = d_errflags_;
           t.lam = (double*)talloc(sizeof(double) * chi);
           envs.push_back({k, s, (int)p, de, (int)mt.size()});
           mt.push_back(t);
@@ -1577,7 +1583,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         full = std::min(full, std::min<long long>(ext, nn[2 * k + s]) * phys_[v]);
       }
       int cap = (int)full;
-      if (ao.maxdim > 0) cap = std::min(cap, std::max(ao.maxdim, std::max(1, ao.mindim)));
+      if (ao.maxdim > 0) cap = std::min(cap, std::max(ao.maxdim, 1));
       keep_cap[k] = cap;
       SuGateTask& t = st[k];
       std::memset(&t, 0, sizeof(t));
@@ -1620,18 +1626,20 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         }
       int maxn_g = 0;
       for (auto& h : ht) maxn_g = std::max(maxn_g, h.n);
-      if (nm > 0 && use_chol_ && maxn_g <= 96) {
-        // Cholesky-preconditioned eigendecomposition (kernels_small.cuh): L in shared memory, Jacobi on L without V
+      if (nm > 0 && use_chol_ && maxn_g <= 256) {
+        // Cholesky-preconditioned eigendecomposition (kernels_small.cuh): L in shared memory (n ≤ 96) or in an
+        // L2-resident global scratch matrix (χ = 64 gives n = d·χ = 128), Jacobi on L without V
+        const bool globg = maxn_g > 96;
         std::vector<CholTask> ct(2 * nm);
         for (int j = 0; j < 2 * nm; ++j) {
           ct[j].G = ht[j].G; ct[j].A = ht[j].A; ct[j].V = ht[j].V; ct[j].n = ht[j].n;
           ct[j].piv = (int*)talloc(sizeof(int) * ht[j].n);
           ct[j].sval = jg[j].sval;
-          ct[j].scratch = nullptr;
+          ct[j].scratch = globg ? (double2*)talloc((size_t)ht[j].n * ht[j].n * sizeof(double2)) : nullptr;
           jg[j].V = nullptr;
         }
         CholTask* dc = upload(ct);
-        const size_t sm = (size_t)maxn_g * maxn_g * sizeof(double2) + (size_t)maxn_g * (sizeof(double) + sizeof(int));
+        const size_t sm = (globg ? 0 : (size_t)maxn_g * maxn_g * sizeof(double2)) + (size_t)maxn_g * (sizeof(double) + sizeof(int));
         chol_prepare_kernel<<<2 * nm, 256, sm, stream_>>>(dc, 1e-15);
         count_launch();
         launch_jacobi(jg, 1e-40);  // the null columns of L are exactly zero
@@ -1718,7 +1726,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         }
         // singular values below 1e-13·‖θ‖_F never survive the truncation (σ² < 1e-26 of the total weight)
         launch_jacobi(jt, 1e-26);
-        su_truncate_kernel<<<(nm + 63) / 64, 64, 0, stream_>>>(ds, nm, ao.maxdim, ao.mindim, ao.cutoff);
+        su_truncate_kernel<<<(nm + 63) / 64, 64, 0, stream_>>>(ds, nm, ao.maxdim, ao.mindim, ao.cutoff, ao.use_absolute_cutoff, ao.use_relative_cutoff);
         count_launch();
         TNQS_CUDA(cudaGetLastError());
       }
@@ -1733,10 +1741,26 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       std::vector<int> keep(ng), flags(2 * std::max<size_t>(1, mt.size()));
       std::vector<double> err(ng);
       std::vector<char> h_rec(rec_bytes * (size_t)R * per);
+      // error words (Jacobi non-convergence, DomainError of a message square root): summed over the ranks BEFORE anyone
+      // reads them, so every rank takes the same decision at the same point and nobody is left inside a collective
+      double h_errflags[2] = {0.0, 0.0};
+      allreduce_sum(d_errflags_, 2);
+      TNQS_CUDA(cudaMemcpyAsync(h_errflags, d_errflags_, sizeof(h_errflags), cudaMemcpyDeviceToHost, stream_));
       TNQS_CUDA(cudaMemcpyAsync(h_rec.data(), d_rec, h_rec.size(), cudaMemcpyDeviceToHost, stream_));
       if (!mt.empty())
         TNQS_CUDA(cudaMemcpyAsync(flags.data(), d_flags, sizeof(int) * 2 * mt.size(), cudaMemcpyDeviceToHost, stream_));
       { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaStreamSynchronize(stream_)); }
+      if (h_errflags[0] != 0.0 || h_errflags[1] != 0.0) {
+        TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
+        free_temps();
+        if (h_errflags[1] != 0.0) {
+          std::string where;
+          for (size_t i = 0; i < mt.size(); ++i)
+            if (flags[2 * i + 1]) { where = " (message into vertex " + std::to_string(verts[2 * gate_ids[gpos + envs[i].gate] + envs[i].site]) + ")"; break; }
+          throw Error(TNQS_EDOMAIN, "DomainError: sqrt of a negative message eigenvalue" + where);
+        }
+        throw Error(TNQS_ECUDA, "simple update: a one-sided Jacobi factorisation did not converge within 40 sweeps");
+      }
       for (int k = 0; k < ng; ++k) {
         const char* rec = h_rec.data() + rec_bytes * (size_t)slot(k);
         std::memcpy(&err[k], rec, sizeof(double));
@@ -1746,12 +1770,6 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           throw Error(TNQS_ECUDA, "simple update: invalid kept rank returned by the truncation kernel");
         }
       }
-      for (size_t i = 0; i < mt.size(); ++i)
-        if (flags[2 * i + 1]) {
-          free_temps();
-          throw Error(TNQS_EDOMAIN, "DomainError: sqrt of a negative message eigenvalue (message into vertex " +
-                                        std::to_string(verts[2 * gate_ids[gpos + envs[i].gate] + envs[i].site]) + ")");
-        }
       if (nm > 0) {
         if (c64()) su_factors_kernel<float><<<nm, 256, 0, stream_>>>(ds);
         else su_factors_kernel<double><<<nm, 256, 0, stream_>>>(ds);
@@ -1860,8 +1878,9 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
   WallScope ws(&stats_.wall_ms, &wall_depth_);
   TNQS_CUDA(cudaSetDevice(device_));
   check_shapes();
-  tnqs_apply_opts ao{0, 1, -1.0, 1, -1.0};
+  tnqs_apply_opts ao{0, 1, -1.0, 1, -1.0, 0, 1, 0, 0};
   if (aop) ao = *aop;
+  if (ao.svd_alg < 0 || ao.svd_alg > 2) throw Error(TNQS_EINVAL, "unknown SVD algorithm");
   if (ao.mindim < 1) ao.mindim = 1;
   // validate everything before touching the state (apply_gates.jl:109-120)
   std::vector<size_t> mat_off(ngates);

@@ -105,6 +105,7 @@ class Engine {
   std::vector<int> msg_next_dim_;
   std::vector<std::vector<int>> sshape_;  // bond-leg dims each site buffer was written with
   std::vector<char> msg_set_;   // 0: identity default (messages(bpc) is empty for it)
+  double* d_errflags_ = nullptr;  // [0] Jacobi non-convergence, [1] DomainError; summed over ranks before the host reads them
   cudaStream_t stream_ = nullptr;
   cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   std::vector<void*> temps_;    // stream-ordered temporaries freed by free_temps()

@@ -51,7 +51,7 @@ __device__ __forceinline__ void rr_pair(int ne, int step, int pair, int& p, int&
 template <int LPP, int RPL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const JacobiTask* __restrict__ tasks, JacobiAux* __restrict__ aux,
                                                              int BC, int C, int ld, int max_sweeps, double tol,
-                                                             double dead_rel2) {
+                                                             double dead_rel2, double* __restrict__ nonconv) {
   extern __shared__ __align__(16) unsigned char jsm_raw[];
   double2* cols = reinterpret_cast<double2*>(jsm_raw);  // [2·BC][ld]
   __shared__ unsigned char s_dead[64];
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const Jacobi
   // ---- sweeps ------------------------------------------------------------------------------------------
   int sweep = 0;
   if (n >= 2) {
+    bool conv = false;
     for (; sweep < max_sweeps; ++sweep) {
       if (tid == 0) s_rot = 0;
       for (int bt = 0; bt < nb - 1; ++bt) {
@@ -274,8 +275,9 @@ __global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const Jacobi
       int rot;
       if (C > 1) rot = __ldcg(&ax->rot[sweep]);
       else { rot = s_rot; if (tid == 0 && rot) ax->rot[sweep] = 1; __syncthreads(); }
-      if (!rot) { ++sweep; break; }
+      if (!rot) { ++sweep; conv = true; break; }
     }
+    if (!conv && crank == 0 && tid == 0 && nonconv) nonconv[0] = 1.0;  // still rotating after max_sweeps: reported to the host
   }
   // ---- singular values (column norms of the A part) and their descending order --------------------------
   // after the last block-round (or, for C == 1, always) this CTA's columns are in shared memory

@@ -47,7 +47,7 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // pair costs one L2 round trip (all loads issued back to back) instead of one per row chunk.
 template <int RPL>
 __global__ void __launch_bounds__(RPL <= 4 ? 1024 : (RPL == 8 ? 512 : 256)) jacobi_kernel(const JacobiTask* __restrict__ tasks,
-                                                      int max_sweeps, double tol) {
+                                                      int max_sweeps, double tol, double* __restrict__ nonconv) {
   const JacobiTask t = tasks[blockIdx.x];
   const int n = t.n, m = t.m;
   const int ne = n + (n & 1);
@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(RPL <= 4 ? 1024 : (RPL == 8 ? 512 : 256)) jaco
   }
   const double floor2 = s_floor;
   if (n >= 2) {
+    bool conv = false;
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
       if (threadIdx.x == 0) s_rot = 0;
       __syncthreads();
@@ -162,8 +163,9 @@ __global__ void __launch_bounds__(RPL <= 4 ? 1024 : (RPL == 8 ? 512 : 256)) jaco
       }
       const int rot = s_rot;
       __syncthreads();
-      if (!rot) break;
+      if (!rot) { conv = true; break; }
     }
+    if (!conv && threadIdx.x == 0 && nonconv) nonconv[0] = 1.0;  // still rotating after max_sweeps: reported to the host
   }
   // column norms, then rank sort (descending, ties by index)
   for (int j = warp; j < n; j += nwarps) {
@@ -196,6 +198,7 @@ struct MsgEigTask {
   void* proj;      // out: Q 1[kept] Q†, row-major, tensor scalar type
   int chi;
   int* flags;      // out: [0] = projector is the identity, [1] = DomainError (negative eigenvalue ≥ cutoff)
+  double* errflags;  // engine-wide error words ([1] is raised on a DomainError), all-reduced across ranks before the host reads them
   double* lam;     // work [χ]
 };
 
@@ -255,7 +258,7 @@ __global__ void msg_finish_kernel(const MsgEigTask* __restrict__ tasks, double c
     S[idx] = s; P[idx] = p;
   }
   __syncthreads();
-  if (threadIdx.x == 0) { t.flags[0] = s_allkept; t.flags[1] = s_domain; }
+  if (threadIdx.x == 0) { t.flags[0] = s_allkept; t.flags[1] = s_domain; if (s_domain && t.errflags) t.errflags[1] = 1.0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -590,8 +593,12 @@ __global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tol
 }
 
 // NDTensors truncate! on P = σ² (simple_update.jl:53-59): maxdim first, then the relative cutoff
+// NDTensors `truncate!` on P = σ² (called through factorize_svd, simple_update.jl:53-59): drop from the tail while
+// n > maxdim (whatever mindim says); then either the absolute test (P[n] ≤ cutoff, truncerr left unscaled) or the
+// summed test (discarded + P[n] ≤ cutoff·scale, scale = ΣP with use_relative_cutoff, else 1; truncerr /= scale),
+// both only while n > mindim.
 __global__ void su_truncate_kernel(const SuGateTask* __restrict__ tasks, int ntasks, int maxdim,
-                                   int mindim, double cutoff) {
+                                   int mindim, double cutoff, int use_abs, int use_rel) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= ntasks) return;
   const SuGateTask& t = tasks[g];
@@ -603,24 +610,33 @@ __global__ void su_truncate_kernel(const SuGateTask* __restrict__ tasks, int nta
     t.sigma[k] = s;
     if (k < full) total += s * s;
   }
-  const double scale = total > 0 ? total : 1.0;
   int keep = full;
   double disc = 0;
   if (mindim < 1) mindim = 1;
-  if (maxdim > 0) {
-    const int lim = maxdim > mindim ? maxdim : mindim;
-    while (keep > lim && keep > 0) { const double s = t.sigma[keep - 1]; disc += s * s; --keep; }
+  if (maxdim > 0)
+    while (keep > maxdim && keep > 1) { const double s = t.sigma[keep - 1]; disc += s * s; --keep; }
+  double err;
+  if (use_abs) {
+    if (cutoff >= 0)
+      while (keep > mindim) {
+        const double s = t.sigma[keep - 1];
+        if (s * s <= cutoff) { disc += s * s; --keep; } else break;
+      }
+    err = disc;
+  } else {
+    const double scale = use_rel ? (total > 0 ? total : 1.0) : 1.0;
+    if (cutoff >= 0)
+      while (keep > mindim) {
+        const double s = t.sigma[keep - 1];
+        if (disc + s * s <= cutoff * scale) { disc += s * s; --keep; } else break;
+      }
+    err = disc / scale;
   }
-  if (cutoff >= 0) {
-    while (keep > mindim) {
-      const double s = t.sigma[keep - 1];
-      if (disc + s * s <= cutoff * scale) { disc += s * s; --keep; } else break;
-    }
-  }
+  if (full <= 1) err = 0.0;  // a single candidate is never truncated
   double kept = 0;
   for (int k = 0; k < keep; ++k) kept += t.sigma[k] * t.sigma[k];
   *t.keep = keep;
-  *t.err = disc / scale;
+  *t.err = err;
   *t.sumsq_kept = kept;
 }
 

@@ -33,7 +33,7 @@ def test_library_exports_every_header_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.ApplyOpts) == 32
+    assert C.sizeof(_lib.ApplyOpts) == 48
     assert C.sizeof(_lib.BpOpts) == 40
     assert C.sizeof(_lib.BpReport) == 16
     assert C.sizeof(_lib.Stats) == 152

@@ -163,6 +163,39 @@ def test_single_two_site_gate(dtype, tol, gate):
 
 
 @pytest.mark.parametrize("dtype,tol", DT)
+@pytest.mark.parametrize("kw", [dict(maxdim=3, cutoff=1e-3, use_absolute_cutoff=True),
+                                dict(cutoff=3e-2, use_relative_cutoff=False),
+                                dict(cutoff=1e-3, use_absolute_cutoff=True, mindim=3),
+                                dict(maxdim=2, mindim=3, cutoff=1e-12),
+                                dict(maxdim=3, cutoff=1e-12, alg="qr_iteration")])
+def test_factorize_svd_keywords(dtype, tol, kw):
+    """The keywords `simple_update` forwards to `factorize_svd` (simple_update.jl:53-59): `use_absolute_cutoff`,
+    `use_relative_cutoff`, `mindim` (maxdim wins: NDTensors `truncate!` drops to maxdim before it looks at mindim)
+    and `alg`, against the oracle's restatement of NDTensors `truncate!`."""
+    g = tq.named_grid((3, 2))
+    dims = [2, 3, 2, 3, 2, 3, 2][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=61)
+    ms = random_psd_messages(g, dims, dtype, seed=62)
+    a, b = g.edges[3]
+    bpc = tq.BeliefPropagationCache(psi)
+    bpc.setmessages(list(ms), list(ms.values()))
+    kw = dict(kw, normalize_tensors=True)
+    out, errs = tq.apply_gates([("Rxxyy", [a, b], 0.9)], bpc, apply_kwargs=kw, update_cache=False)
+    c = oracle_from_tns(psi)
+    for (x, y), m in ms.items():
+        c.msg[(g.index[x], g.index[y])] = m
+    gm, gv = circuit_for_oracle(g, [("Rxxyy", [a, b], 0.9)])
+    c, oerrs, _ = orc.apply_gates(c, gm, gv, [], kw, update_cache=False)
+    assert out.bond_dims()[3] == c.bond_dims()[3]
+    assert abs(errs[0] - oerrs[0]) <= 200 * tol * max(oerrs[0], 1e-3)
+    assert rel(np.diag(out.message((a, b))), np.diag(c.msg[(g.index[a], g.index[b])])) < 100 * tol
+    with pytest.raises(tq.ArgumentError):
+        tq.apply_gates([("Rzz", [a, b], 0.1)], bpc, apply_kwargs=dict(alg="bogus"))
+    with pytest.raises(tq.ArgumentError):
+        tq.apply_gates([("Rzz", [a, b], 0.1)], bpc, apply_kwargs=dict(ortho="left"))
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
 def test_tfim_layers_small_grid(dtype, tol):
     # test_apply.jl:23-53 flavour with truncation: per-gate truncerr, ⟨Z⟩, bond dims, messages
     g = tq.named_grid((3, 3))

@@ -358,3 +358,20 @@ def test_multi_site_expect_exact_on_tree():
     # adjacent pair: agrees with the dedicated two-site routine
     (a, b) = g.edge_uv()[0]
     assert abs(orc.expect_region(c, [a, b], {a: Zm, b: Zm}) - orc.expect_two_site(c, a, b, Zm, Zm)) < 1e-12
+
+
+def test_truncate_spectrum_follows_ndtensors_truncate():
+    """NDTensors `truncate!` as summarised in SURVEY.md §8a: maxdim first (whatever mindim says), then the summed
+    relative test, or the per-weight absolute test with an unscaled truncation error."""
+    p = np.array([4.0, 2.0, 1.0, 0.5, 0.25, 0.125])
+    tot = p.sum()
+    assert orc.truncate_spectrum(p, 3, None) == (3, (0.5 + 0.25 + 0.125) / tot)
+    assert orc.truncate_spectrum(p, 2, None, mindim=4) == (2, (1.0 + 0.5 + 0.25 + 0.125) / tot)  # maxdim wins
+    n, e = orc.truncate_spectrum(p, None, 0.4 / tot)  # summed relative test: 0.125 + 0.25 = 0.375 ≤ 0.4 < 0.875
+    assert n == 4 and abs(e - 0.375 / tot) < 1e-15
+    assert orc.truncate_spectrum(p, None, 0.4 / tot, mindim=5)[0] == 5
+    n, e = orc.truncate_spectrum(p, None, 0.5, use_absolute_cutoff=True)  # per-weight test, error unscaled
+    assert n == 3 and abs(e - 0.875) < 1e-15
+    n, e = orc.truncate_spectrum(p, None, 0.4, use_relative_cutoff=False)  # summed test against 1
+    assert n == 4 and abs(e - 0.375) < 1e-15
+    assert orc.truncate_spectrum(np.array([3.0]), 1, 1.0) == (1, 0.0)

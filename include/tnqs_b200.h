@@ -154,6 +154,13 @@ int  tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* 
 int  tnqs_apply_leg_matrices(tnqs_handle h, int n, const int32_t* verts, const int32_t* nbrs,
                              const double* mats);
 
+/* random_tensornetworkstate(eltype, g; bond_dimension) (src/TensorNetworks/tensornetworkstate.jl:93-103) generated in place
+ * on the device: every site tensor of the handle (created with the wanted bond dimensions) is filled with iid
+ * N(0,1) + i N(0,1) entries from a counter-based generator keyed by (seed, vertex); normalize != 0 scales each tensor to
+ * unit Frobenius norm.  All messages return to their identity default.  The RNG stream is this library's own (Julia's
+ * is not reproducible outside Julia). */
+int  tnqs_randomize_sites(tnqs_handle h, uint64_t seed, int normalize);
+
 /* --- multi-GPU: vertex ownership + NCCL exchange --------------------------- */
 
 /* Join an NCCL communicator: every rank holds the full graph, owns the site tensors of the

@@ -8,7 +8,7 @@ from .graphs import (NamedGraph, named_grid, named_path_graph, named_comb_tree, 
 from .gates import (ArgumentError, gate_matrix, observable_matrix, register_gate, register_alias,  # noqa: F401
                     unregister_gate)
 from .api import (TensorNetworkState, BeliefPropagationCache, tensornetworkstate, zerostate,  # noqa: F401
-                  random_tensornetworkstate, apply_gates, apply_circuit, truncate, update, expect, network,
+                  random_tensornetworkstate, random_bpc_on_device, apply_gates, apply_circuit, truncate, update, expect, network,
                   maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays,
                   vertex_scalar, vertex_scalars, edge_scalar, edge_scalars, scalar_factors_quotient, freenergy,
                   partitionfunction, rescale_messages, rescale_vertices, rescale, norm_sqr, normalize,

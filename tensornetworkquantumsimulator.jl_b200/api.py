@@ -100,6 +100,41 @@ def random_tensornetworkstate(eltype, g: NamedGraph, bond_dimension: int = 1, d:
     return TensorNetworkState(g, tensors, eltype)
 
 
+def random_bpc_on_device(eltype, g: NamedGraph, bond_dimension: int = 1, d: int = 2, seed: int = 1234, device: int = 0,
+                         normalize: bool = True, shard_fn=None) -> "BeliefPropagationCache":
+    """`BeliefPropagationCache(random_tensornetworkstate(eltype, g; bond_dimension))` with the tensors generated on
+    the device (`tnqs_randomize_sites`): iid normal entries keyed by (seed, vertex), each tensor scaled to unit
+    Frobenius norm when `normalize`.  For synthetic states too large to build on the host (16×16 at χ=64 is 53 GB).
+    `shard_fn(bpc)` (e.g. `tnqs_b200.shard`) is applied before the tensors are filled, so each rank generates only
+    the tensors it owns."""
+    lib = _lib.load()
+    uv = np.array(g.edge_uv(), dtype=np.int32).reshape(-1, 2)
+    phys = np.full(g.nv, d, dtype=np.int32)
+    bond = np.full(g.ne, bond_dimension, dtype=np.int32)
+    h = C.c_void_p()
+    _, uv_p = _i32(uv)
+    _, ph_p = _i32(phys)
+    _, bo_p = _i32(bond)
+    if shard_fn is None:
+        _lib.check(lib.tnqs_create(_DT[np.dtype(eltype)], g.nv, g.ne, uv_p, ph_p, bo_p, device, C.byref(h)))
+        bpc = BeliefPropagationCache(None, device, _handle=h, _graph=g, _dtype=np.dtype(eltype), _seq=None)
+    else:
+        # create at bond dimension 1 (tiny), shard, then declare the real shapes: only the owner allocates a tensor
+        one = np.ones(g.ne, dtype=np.int32)
+        _, one_p = _i32(one)
+        _lib.check(lib.tnqs_create(_DT[np.dtype(eltype)], g.nv, g.ne, uv_p, ph_p, one_p, device, C.byref(h)))
+        bpc = BeliefPropagationCache(None, device, _handle=h, _graph=g, _dtype=np.dtype(eltype), _seq=None)
+        shard_fn(bpc)
+        for i, v in enumerate(g.vertices()):
+            shp = np.array((d,) + (bond_dimension,) * len(g.incident[i]), dtype=np.int64)
+            owned = bpc.owner[i] == bpc.rank
+            buf = np.zeros(int(np.prod(shp)) if owned else 1, dtype=eltype)
+            _lib.check(lib.tnqs_set_site(h, i, buf.ctypes.data_as(C.c_void_p), len(shp), shp.ctypes.data_as(C.POINTER(C.c_int64))))
+    bpc.set_edge_sequence(forest_cover_edge_sequence(g))
+    _lib.check(lib.tnqs_randomize_sites(bpc._h, C.c_uint64(int(seed)), int(bool(normalize))))
+    return bpc
+
+
 class BeliefPropagationCache:
     """Device-resident `BeliefPropagationCache` (`beliefpropagationcache.jl:9-15`): site tensors and
     messages live in HBM behind a `tnqs_handle`; constructing it runs no BP and leaves every message

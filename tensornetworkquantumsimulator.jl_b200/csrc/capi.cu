@@ -143,6 +143,9 @@ int tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* f
     E(h).scale_sites(n, verts, factors);
   });
 }
+int tnqs_randomize_sites(tnqs_handle h, uint64_t seed, int normalize) {
+  return guarded([&] { E(h).randomize_sites((unsigned long long)seed, normalize); });
+}
 int tnqs_apply_leg_matrices(tnqs_handle h, int n, const int32_t* verts, const int32_t* nbrs, const double* mats) {
   return guarded([&] {
     if (n > 0 && (!verts || !nbrs || !mats)) throw Error(TNQS_EINVAL, "null argument");

@@ -2093,6 +2093,38 @@ void Engine::scale_sites(int n, const int32_t* verts, const double* factors) {
   TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
+// random_tensornetworkstate (tensornetworkstate.jl:93-103) generated in place on the device: iid 𝒩(0,1) + i𝒩(0,1) entries
+// from a counter-based generator keyed by (seed, vertex), optionally scaled to unit Frobenius norm per tensor.  Messages
+// fall back to their identity default.  Sharded caches fill only the tensors they own (same values on any rank count).
+void Engine::randomize_sites(unsigned long long seed, int normalize) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  delete_messages();
+  std::vector<RandTask> t;
+  std::vector<int> vs;
+  long long maxn = 0;
+  for (int v = 0; v < nv_; ++v) {
+    if (!owns(v) || !site_[v]) continue;
+    RandTask r{site_[v], site_elems(v), seed * 0x2545F4914F6CDD1Dull + (unsigned long long)v * 0x9E3779B97F4A7C15ull};
+    t.push_back(r); vs.push_back(v);
+    maxn = std::max(maxn, r.n);
+  }
+  if (!t.empty()) {
+    RandTask* d = upload(t);
+    const int nb = (int)std::max<long long>(1, std::min<long long>(1024, (maxn + 1023) / 1024));
+    for (int off = 0; off < (int)t.size(); off += 65535) {
+      const int cnt = std::min(65535, (int)t.size() - off);
+      if (c64()) randn_kernel<float><<<dim3(nb, cnt), 256, 0, stream_>>>(d + off);
+      else randn_kernel<double><<<dim3(nb, cnt), 256, 0, stream_>>>(d + off);
+      count_launch();
+    }
+    TNQS_CUDA(cudaGetLastError());
+    if (normalize) normalize_sites(vs);
+  }
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+}
+
 // tn[v] ← tn[v] ×_{leg(v,nbr)} M for a list of (v, nbr, M): M is χ×χ row-major [in][out] complex128.  Bond
 // dimensions do not change.  Used by symmetric_gauge (symmetric_gauge.jl:1-56) and other host-driven regauging.
 void Engine::apply_leg_matrices(int n, const int32_t* verts, const int32_t* nbrs, const double* mats) {

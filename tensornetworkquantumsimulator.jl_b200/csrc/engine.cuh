@@ -78,6 +78,7 @@ class Engine {
   void expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out);
   void vertex_scalars(int n, const int32_t* verts, double* out);
   void scale_sites(int n, const int32_t* verts, const double* factors);
+  void randomize_sites(unsigned long long seed, int normalize);
   void apply_leg_matrices(int n, const int32_t* verts, const int32_t* nbrs, const double* mats);
 
   // multi-GPU: vertex ownership + NCCL exchange of the replicated small data (messages, Gram matrices)

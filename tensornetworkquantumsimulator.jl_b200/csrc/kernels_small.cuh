@@ -771,4 +771,33 @@ __global__ void __launch_bounds__(256) bp_finalize_kernel(const BpFinTask* __res
   if (threadIdx.x == 0) *t.diff = 1.0 - (dx * dx + dy * dy) / (na * nb);
 }
 
+// ------------------------------------------------------------------------------------------------
+// random_tensornetworkstate on the device (tensornetworkstate.jl:93-103: iid normal entries): a counter-based
+// generator (SplitMix64 of (seed, vertex, element) → Box–Muller), so the state depends only on the seed
+// ------------------------------------------------------------------------------------------------
+struct RandTask { void* data; long long n; unsigned long long key; };
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+template <typename R>
+__global__ void __launch_bounds__(256) randn_kernel(const RandTask* __restrict__ tasks) {
+  using C = typename Cx<R>::type;
+  const RandTask t = tasks[blockIdx.y];
+  C* __restrict__ out = (C*)t.data;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < t.n; i += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long h = splitmix64(t.key ^ splitmix64((unsigned long long)i));
+    const double u1 = ((double)(h >> 40) + 0.5) * (1.0 / 16777216.0);          // (0,1), 24 bits
+    const double u2 = ((double)((h >> 8) & 0xFFFFFFull)) * (1.0 / 16777216.0);  // [0,1)
+    const double r = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    C z;
+    z.x = (R)(r * cs); z.y = (R)(r * sn);
+    out[i] = z;
+  }
+}
+
 }  // namespace tnqs

@@ -154,6 +154,16 @@ int  tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* 
 int  tnqs_apply_leg_matrices(tnqs_handle h, int n, const int32_t* verts, const int32_t* nbrs,
                              const double* mats);
 
+/* One site of a multi-site region contraction — expect(alg"bp") over a Steiner path (src/expect.jl:59-82) and
+ * reduced_density_matrix(alg"bp") (src/rdm.jl:52-73).  The ket tensor of vertex v absorbs, on every bond leg except the one
+ * towards `open_nbr`, either custom_mats[i] (χ×χ complex128 row-major [ket][bra], for the leg towards custom_nbrs[i]: the
+ * partial contraction arriving from the previous site of the path) or that leg's BP message; `op` (d×d complex128 row-major
+ * O[s'][s], or NULL) acts on the physical index; the result is contracted with conj(T_v) over all closed indices.
+ * out[ket][bra], n×n complex128: n = d·χ (open_phys=1, open_nbr>=0: E[(s,b),(s',b')]), χ (open_phys=0) or d (open_nbr<0).
+ * The host walks the path with it (api.py: expect / reduced_density_matrix). */
+int  tnqs_site_contract(tnqs_handle h, int v, int n_custom, const int32_t* custom_nbrs, const double* custom_mats,
+                        int open_nbr, int open_phys, const double* op, double* out, int64_t capacity, int* n_out);
+
 /* random_tensornetworkstate(eltype, g; bond_dimension) (src/TensorNetworks/tensornetworkstate.jl:93-103) generated in place
  * on the device: every site tensor of the handle (created with the wanted bond dimensions) is filled with iid
  * N(0,1) + i N(0,1) entries from a counter-based generator keyed by (seed, vertex); normalize != 0 scales each tensor to

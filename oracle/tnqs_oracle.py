@@ -649,6 +649,45 @@ def expect_region(c: OracleCache, region: Sequence[int], ops: Dict[int, np.ndarr
     return coeff * np.sum(op * rho.T) / np.trace(rho)
 
 
+def rdm_region(c: OracleCache, vs: Sequence[int], normalize: bool = True) -> np.ndarray:
+    """`reduced_density_matrix(Algorithm"bp", cache, vs)` (src/rdm.jl:52-73): tensors of the Steiner region of `vs`
+    (one vertex, or the shortest path between two), their conjugates and the incoming messages contracted exactly with
+    the physical legs of `vs` left open; ρ[(s_1 s_2), (s_1' s_2')], trace-normalised (`normalize_rdm`)."""
+    vs = list(vs)
+    region = vs if len(vs) == 1 else steiner_path(c, vs[0], vs[1])
+    inside = set(region)
+    wide = _wide(c.dtype)
+    letters = iter("abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ")
+    bond_letter: Dict[int, str] = {}
+    phys_letter: Dict[int, str] = {}
+    ext: List[Tuple[str, int, int]] = []
+    subs = []
+    for v in region:
+        phys_letter[v] = next(letters)
+        sub = phys_letter[v]
+        for e, w in c.incident[v]:
+            if w in inside:
+                if e not in bond_letter:
+                    bond_letter[e] = next(letters)
+                sub += bond_letter[e]
+            else:
+                l = next(letters)
+                ext.append((l, v, w))
+                sub += l
+        subs.append(sub)
+    # open physical legs of vs first (in the order given), then the traced ones, then the external bonds
+    closed = [v for v in region if v not in vs]
+    out_sub = "".join(phys_letter[v] for v in vs) + "".join(phys_letter[v] for v in closed) + "".join(l for l, _, _ in ext)
+    psi = np.einsum(",".join(subs) + "->" + out_sub, *[c.T[v].astype(wide) for v in region], optimize=True)
+    n = len(region)
+    ket = psi
+    for k, (_, v, w) in enumerate(ext):
+        ket = np.moveaxis(np.tensordot(ket, c.message(w, v).astype(wide), axes=([n + k], [0])), -1, n + k)
+    dopen = int(np.prod(psi.shape[:len(vs)]))
+    rho = ket.reshape(dopen, -1) @ psi.reshape(dopen, -1).conj().T
+    return rho / np.trace(rho) if normalize else rho
+
+
 def to_statevector(c: OracleCache) -> np.ndarray:
     """Contract the whole TNS into a dense vector ψ[s_0, …, s_{nv-1}] (small systems only)."""
     letters = "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ"

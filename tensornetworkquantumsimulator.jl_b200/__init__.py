@@ -12,6 +12,6 @@ from .api import (TensorNetworkState, BeliefPropagationCache, tensornetworkstate
                   maxvirtualdim, messages, message, default_bp_update_kwargs, circuit_arrays,
                   vertex_scalar, vertex_scalars, edge_scalar, edge_scalars, scalar_factors_quotient, freenergy,
                   partitionfunction, rescale_messages, rescale_vertices, rescale, norm_sqr, normalize,
-                  renyi_entropy, von_neumann_entanglement_entropy, symmetric_gauge, symmetrize_and_normalize)
+                  renyi_entropy, von_neumann_entanglement_entropy, reduced_density_matrix, steiner_path, symmetric_gauge, symmetrize_and_normalize)
 from ._lib import TnqsError, LIB_PATH  # noqa: F401
 from .distributed import partition_vertices, cut_edges, shard  # noqa: F401

@@ -48,7 +48,7 @@ class TnqsError(RuntimeError):
 SYMBOLS = ["tnqs_create", "tnqs_clone", "tnqs_destroy", "tnqs_set_site", "tnqs_site_shape",
            "tnqs_get_site", "tnqs_set_message", "tnqs_get_message", "tnqs_delete_messages",
            "tnqs_get_bond_dims", "tnqs_set_edge_sequence", "tnqs_apply_gates", "tnqs_bp_update",
-           "tnqs_expect_local", "tnqs_expect_two_site", "tnqs_vertex_scalars", "tnqs_scale_sites", "tnqs_randomize_sites", "tnqs_apply_leg_matrices", "tnqs_comm_unique_id", "tnqs_comm_init",
+           "tnqs_expect_local", "tnqs_expect_two_site", "tnqs_vertex_scalars", "tnqs_scale_sites", "tnqs_randomize_sites", "tnqs_site_contract", "tnqs_apply_leg_matrices", "tnqs_comm_unique_id", "tnqs_comm_init",
            "tnqs_get_stats", "tnqs_set_profiling", "tnqs_last_error", "tnqs_version"]
 
 _lib = None
@@ -85,6 +85,7 @@ def load():
         "tnqs_vertex_scalars": [vp, C.c_int, i32p, dp],
         "tnqs_scale_sites": [vp, C.c_int, i32p, dp],
         "tnqs_randomize_sites": [vp, C.c_uint64, C.c_int],
+        "tnqs_site_contract": [vp, C.c_int, C.c_int, i32p, dp, C.c_int, C.c_int, dp, dp, C.c_int64, ip],
         "tnqs_apply_leg_matrices": [vp, C.c_int, i32p, i32p, dp],
         "tnqs_comm_unique_id": [vp],
         "tnqs_comm_init": [vp, C.c_int, C.c_int, C.c_char_p, i32p],

@@ -703,14 +703,89 @@ def _collect_observable(obs, g: NamedGraph):
     return ops, verts, coeff
 
 
-def expect(psi, observable, alg: Optional[str] = "bp", **cache_update_kwargs):
-    """`expect(ψ | ψ_bpc, obs; alg="bp")` (`expect.jl:54-82,114-135`).  `obs = (ops, vertices[,
-    coeff])` or a list of them.  Device path: single-site and adjacent two-site observables."""
+def steiner_path(g: NamedGraph, terminals: Sequence) -> Optional[List]:
+    """The Steiner tree of `terminals` (`expect.jl:67`, `rdm.jl:58`: `steiner_tree(network(cache), vs)`) when it is a
+    simple path: shortest paths (BFS, neighbours in incidence order) between consecutive terminals, ordered along the
+    path.  For two terminals this is the reference's region; returns None when the union is not a simple path."""
+    idx = [g.index[v] for v in terminals]
+
+    def bfs(a, b):
+        prev = {a: -1}
+        queue = [a]
+        while queue:
+            x = queue.pop(0)
+            if x == b:
+                break
+            for _, w in g.incident[x]:
+                if w not in prev:
+                    prev[w] = x
+                    queue.append(w)
+        path = [b]
+        while path[-1] != a:
+            path.append(prev[path[-1]])
+        return path[::-1]
+
+    # order the terminals along a path: start from one end of the two farthest-apart terminals
+    if len(idx) == 2:
+        order = idx
+    else:
+        dist = {(a, b): len(bfs(a, b)) for a in idx for b in idx if a != b}
+        a0, _ = max(dist, key=dist.get)
+        order = sorted(idx, key=lambda t: 0 if t == a0 else dist[(a0, t)])
+    path = [order[0]]
+    for a, b in zip(order[:-1], order[1:]):
+        path += bfs(a, b)[1:]
+    if len(set(path)) != len(path):
+        return None
+    return path
+
+
+def _site_contract(bpc: "BeliefPropagationCache", v: int, custom: Dict[int, np.ndarray], open_nbr: int, open_phys: bool,
+                   op: Optional[np.ndarray]) -> np.ndarray:
+    """`tnqs_site_contract`: one site of a path-region contraction; returns the n×n complex128 matrix out[ket][bra]."""
+    lib = bpc._lib
+    nb = np.array(list(custom.keys()), dtype=np.int32)
+    mats = (np.concatenate([np.ascontiguousarray(m, dtype=np.complex128).reshape(-1) for m in custom.values()]).view(np.float64)
+            if custom else np.zeros(0))
+    d = 2
+    chi_max = int(max(bpc.bond_dims())) if bpc.graph.ne else 1
+    cap = (4 * chi_max) ** 2
+    out = np.zeros(cap, dtype=np.complex128)
+    n = C.c_int(0)
+    nb_a, nb_p = _i32(nb)
+    m_a, m_p = _f64(mats)
+    op_p = None
+    if op is not None:
+        op_a = np.ascontiguousarray(op, dtype=np.complex128)
+        op_p = op_a.ctypes.data_as(C.POINTER(C.c_double))
+    _lib.check(lib.tnqs_site_contract(bpc._h, int(v), len(nb), nb_p if len(nb) else None, m_p if len(nb) else None,
+                                      int(open_nbr), int(bool(open_phys)), op_p, out.ctypes.data_as(C.POINTER(C.c_double)),
+                                      cap, C.byref(n)))
+    return out[:n.value * n.value].reshape(n.value, n.value).copy()
+
+
+def _path_numerator(bpc: "BeliefPropagationCache", path: List[int], ops: Dict[int, np.ndarray]):
+    """Σ over the path region of ⟨T| ops ⊗ incoming messages |T⟩ (`contract_region`, expect.jl:71-78), walking the path:
+    every site passes a χ×χ partial contraction to the next one as if it were the message on that bond."""
+    L = None
+    for k, v in enumerate(path):
+        custom = {} if L is None else {path[k - 1]: L}
+        if k + 1 < len(path):
+            L = _site_contract(bpc, v, custom, path[k + 1], False, ops.get(v))
+        else:
+            rho = _site_contract(bpc, v, custom, -1, True, ops.get(v))
+            return np.trace(rho)
+
+
+def expect(psi, observable, alg: Optional[str] = "bp", cache_update_kwargs: Optional[dict] = None, device: int = 0):
+    """`expect(ψ | ψ_bpc, obs; alg="bp")` (`expect.jl:54-82,114-135`).  `obs = (ops, vertices[, coeff])` or a list of
+    them.  Device path: single-site, adjacent two-site and — for regions whose Steiner tree is a path — multi-site
+    observables (`expect.jl:67-81`)."""
     if alg != "bp":
         raise RuntimeError("Expected alg = \"bp\": exact and boundary-MPS contraction are outside the "
                            "accelerated path (export with network(ψ_bpc) and use the reference for those)")
     if isinstance(psi, TensorNetworkState):  # expect.jl:123-135
-        bpc = BeliefPropagationCache(psi)
+        bpc = BeliefPropagationCache(psi, device=device)
         kw = cache_update_kwargs or default_bp_update_kwargs(bpc)
         bpc = update(bpc, inplace=True, **kw)
         return expect(bpc, observable, alg)
@@ -718,7 +793,7 @@ def expect(psi, observable, alg: Optional[str] = "bp", **cache_update_kwargs):
     single = isinstance(observable, tuple)
     obs_list = [observable] if single else list(observable)
     out: List = [None] * len(obs_list)
-    one, two = [], []
+    one, two, many = [], [], []
     for i, obs in enumerate(obs_list):
         ops, verts, coeff = _collect_observable(obs, bpc.graph)
         if coeff == 0:
@@ -728,7 +803,7 @@ def expect(psi, observable, alg: Optional[str] = "bp", **cache_update_kwargs):
         elif len(verts) == 2 and bpc.graph.has_edge(verts[0], verts[1]):
             two.append((i, ops, verts, coeff))
         else:
-            raise NotImplementedError("device expect supports single-site and adjacent two-site observables")
+            many.append((i, ops, verts, coeff))
     lib = bpc._lib
     if one:
         vs_a, vs_p = _i32([bpc.graph.index[o[2][0]] for o in one])
@@ -744,7 +819,57 @@ def expect(psi, observable, alg: Optional[str] = "bp", **cache_update_kwargs):
         _lib.check(lib.tnqs_expect_two_site(bpc._h, len(two), vs_p, m_p, res.ctypes.data_as(C.POINTER(C.c_double))))
         for k, o in enumerate(two):
             out[o[0]] = o[3] * complex(res[2 * k], res[2 * k + 1])
+    for (i, ops, verts, coeff) in many:  # expect.jl:67-81 over a Steiner path
+        if len(set(verts)) != len(verts):
+            raise RuntimeError("Invalid observable: a vertex appears twice.")
+        path = steiner_path(bpc.graph, verts)
+        if path is None:
+            raise NotImplementedError("device expect: the Steiner tree of these vertices is not a path")
+        opm = {bpc.graph.index[v]: observable_matrix(o) for v, o in zip(verts, ops)}
+        numer = _path_numerator(bpc, path, opm)
+        denom = _path_numerator(bpc, path, {})
+        out[i] = coeff * numer / denom
     return out[0] if single else out
+
+
+def reduced_density_matrix(psi, vs, alg: Optional[str] = "bp", normalize: bool = True,
+                           cache_update_kwargs: Optional[dict] = None, device: int = 0) -> np.ndarray:
+    """`reduced_density_matrix(ψ | ψ_bpc, vs; alg="bp", normalize)` (`src/rdm.jl:52-73`): BP reduced density matrix of one
+    vertex, or of two vertices joined through their Steiner path; ρ[(s_1, s_2), (s_1', s_2')] with `vs[0]` the slower
+    index, trace 1 when `normalize` (`normalize_rdm`)."""
+    if alg != "bp":
+        raise RuntimeError("Expected alg = \"bp\" on the device path")
+    if isinstance(psi, TensorNetworkState):
+        bpc = BeliefPropagationCache(psi, device=device)
+        kw = cache_update_kwargs or default_bp_update_kwargs(bpc)
+        bpc = update(bpc, inplace=True, **kw)
+        return reduced_density_matrix(bpc, vs, alg, normalize)
+    bpc: BeliefPropagationCache = psi
+    vs = _as_vertex_list(vs)
+    g = bpc.graph
+    if len(vs) == 1:
+        rho = _site_contract(bpc, g.index[vs[0]], {}, -1, True, None)
+    elif len(vs) == 2:
+        path = steiner_path(g, vs)
+        d = 2
+        # open the first site: E[(s,b),(s',b')]; every (s,s') block is a χ×χ matrix that travels down the path
+        E = _site_contract(bpc, path[0], {}, path[1], True, None)
+        chi = E.shape[0] // d
+        E = E.reshape(d, chi, d, chi)
+        rho = np.zeros((d, d, d, d), dtype=np.complex128)  # [s1, s2, s1', s2']
+        for s in range(d):
+            for sp in range(d):
+                L = np.ascontiguousarray(E[s, :, sp, :])
+                for k in range(1, len(path) - 1):
+                    L = _site_contract(bpc, path[k], {path[k - 1]: L}, path[k + 1], False, None)
+                r2 = _site_contract(bpc, path[-1], {path[-2]: L}, -1, True, None)
+                rho[s, :, sp, :] = r2
+        rho = rho.reshape(d * d, d * d)
+    else:
+        raise NotImplementedError("device reduced_density_matrix supports one or two vertices")
+    if normalize:
+        rho = rho / np.trace(rho)
+    return rho
 
 
 def network(bpc: BeliefPropagationCache) -> TensorNetworkState:

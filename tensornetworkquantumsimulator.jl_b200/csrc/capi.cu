@@ -143,6 +143,13 @@ int tnqs_scale_sites(tnqs_handle h, int n, const int32_t* verts, const double* f
     E(h).scale_sites(n, verts, factors);
   });
 }
+int tnqs_site_contract(tnqs_handle h, int v, int n_custom, const int32_t* custom_nbrs, const double* custom_mats, int open_nbr,
+                       int open_phys, const double* op, double* out, int64_t capacity, int* n_out) {
+  return guarded([&] {
+    if (!out || !n_out || (n_custom > 0 && (!custom_nbrs || !custom_mats))) throw Error(TNQS_EINVAL, "null argument");
+    E(h).site_contract(v, n_custom, custom_nbrs, custom_mats, open_nbr, open_phys, op, out, capacity, n_out);
+  });
+}
 int tnqs_randomize_sites(tnqs_handle h, uint64_t seed, int normalize) {
   return guarded([&] { E(h).randomize_sites((unsigned long long)seed, normalize); });
 }

@@ -2058,6 +2058,81 @@ void Engine::expect_local(int nobs, const int32_t* verts, const double* ops, dou
   }
 }
 
+// One site of a region contraction (expect.jl:59-82 / rdm.jl:52-73 for a region that is a path): the ket tensor of vertex v
+// absorbs, on every bond leg except `open_nbr`, either a caller-supplied matrix (the partial contraction arriving from the
+// previous site of the path) or the BP message of that leg; an optional operator acts on its physical index; the result is
+// contracted with conj(T_v) over everything except the open indices.  out[ket][bra] row-major, complex128:
+//   open_phys = 1, open_nbr = w : E[(s,b),(s',b')], n = d·χ_b     open_phys = 0, open_nbr = w : M[b,b'], n = χ_b
+//   open_phys = 1, open_nbr < 0 : ρ[s,s'], n = d
+void Engine::site_contract(int v, int n_custom, const int32_t* custom_nbrs, const double* custom_mats, int open_nbr, int open_phys,
+                           const double* op, double* out, int64_t cap, int* out_n) {
+  TNQS_CUDA(cudaSetDevice(device_));
+  check_shapes();
+  if (v < 0 || v >= nv_) throw Error(TNQS_EINVAL, "vertex out of range");
+  if (open_nbr < 0 && !open_phys) throw Error(TNQS_EINVAL, "tnqs_site_contract: nothing left open");
+  const int d = phys_[v];
+  int open_pos = -1;
+  if (open_nbr >= 0) open_pos = leg_pos(v, dedge(open_nbr, v) / 2);
+  const int chi_open = open_pos >= 0 ? bond_[inc_[v][open_pos].edge] : 1;
+  const int n = (open_phys ? d : 1) * chi_open;
+  *out_n = n;
+  if (cap < (int64_t)n * n) throw Error(TNQS_ECAPACITY, "tnqs_site_contract: output buffer too small");
+  // device copies of the caller's matrices in the tensor's scalar type
+  auto to_device = [&](const double* src, size_t cnt) -> void* {
+    void* dm = talloc(cnt * esz_);
+    if (c64()) {
+      std::vector<float2> h(cnt);
+      for (size_t k = 0; k < cnt; ++k) { h[k].x = (float)src[2 * k]; h[k].y = (float)src[2 * k + 1]; }
+      TNQS_CUDA(cudaMemcpyAsync(dm, h.data(), cnt * sizeof(float2), cudaMemcpyHostToDevice, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));  // h is a pageable temporary
+    } else {
+      TNQS_CUDA(cudaMemcpyAsync(dm, src, cnt * sizeof(double2), cudaMemcpyHostToDevice, stream_));
+      TNQS_CUDA(cudaStreamSynchronize(stream_));
+    }
+    return dm;
+  };
+  std::vector<Chain> chains(1);
+  chains[0].v = v;
+  std::vector<char> custom_seen(inc_[v].size(), 0);
+  size_t moff = 0;
+  for (int i = 0; i < n_custom; ++i) {
+    const int de = dedge(custom_nbrs[i], v);
+    const int p = leg_pos(v, de / 2);
+    if (p == open_pos) throw Error(TNQS_EINVAL, "tnqs_site_contract: a matrix was supplied for the open leg");
+    if (custom_seen[p]) throw Error(TNQS_EINVAL, "tnqs_site_contract: two matrices for the same leg");
+    custom_seen[p] = 1;
+    const size_t cnt = (size_t)bond_[de / 2] * bond_[de / 2];
+    chains[0].steps.push_back({p, to_device(custom_mats + moff, cnt)});
+    moff += 2 * cnt;
+  }
+  for (size_t p = 0; p < inc_[v].size(); ++p) {
+    if ((int)p == open_pos || custom_seen[p]) continue;
+    const int de = dedge(inc_[v][p].nbr, v);
+    if (!msg_set_[de] || !msg_[de]) continue;  // identity default
+    chains[0].steps.push_back({(int)p, msg_[de]});
+  }
+  if (op) {  // ket ← O·ket: the mode product convention is Out[j'] = Σ_j Mat[j][j']·A[j], so Mat = Oᵀ
+    std::vector<double> ot(2 * (size_t)d * d);
+    for (int a = 0; a < d; ++a)
+      for (int b = 0; b < d; ++b) { ot[2 * (a * d + b)] = op[2 * (b * d + a)]; ot[2 * (a * d + b) + 1] = op[2 * (b * d + a) + 1]; }
+    chains[0].steps.push_back({-1, to_device(ot.data(), (size_t)d * d)});
+  }
+  run_chains(chains);
+  double2* d_out = (double2*)talloc((size_t)n * n * sizeof(double2));
+  TNQS_CUDA(cudaMemsetAsync(d_out, 0, (size_t)n * n * sizeof(double2), stream_));
+  if (owns(v)) {
+    std::vector<GramTask> gt(1);
+    std::vector<double2*> oo(1, d_out);
+    gt[0] = gram_task(v, open_pos, (open_phys && open_pos >= 0) ? d : 1, site_[v], chains[0].result);
+    launch_gram(gt, /*acc_double=*/true, oo, /*transpose=*/true);
+  }
+  allreduce_sum(reinterpret_cast<double*>(d_out), 2 * (size_t)n * n);
+  TNQS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * n * sizeof(double2), cudaMemcpyDeviceToHost, stream_));
+  TNQS_CUDA(cudaStreamSynchronize(stream_));
+  free_temps();
+  release_slabs();
+}
+
 // vertex_scalar(bpc, v) (abstractbeliefpropagationcache.jl:22-28): ⟨T_v| incoming messages |T_v⟩ = tr ρ_v
 void Engine::vertex_scalars(int n, const int32_t* verts, double* out) {
   if (n <= 0) return;

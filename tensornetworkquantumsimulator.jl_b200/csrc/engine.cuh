@@ -77,6 +77,8 @@ class Engine {
   void expect_local(int nobs, const int32_t* verts, const double* ops, double* out);
   void expect_two_site(int nobs, const int32_t* verts, const double* ops, double* out);
   void vertex_scalars(int n, const int32_t* verts, double* out);
+  void site_contract(int v, int n_custom, const int32_t* custom_nbrs, const double* custom_mats, int open_nbr, int open_phys,
+                     const double* op, double* out, int64_t cap, int* out_n);
   void scale_sites(int n, const int32_t* verts, const double* factors);
   void randomize_sites(unsigned long long seed, int normalize);
   void apply_leg_matrices(int n, const int32_t* verts, const int32_t* nbrs, const double* mats);

@@ -526,3 +526,45 @@ def test_device_matches_golden_config1():
         assert np.max(np.abs(errs - np.array(ref["trunc_err"]))) < 1e-7 * max(1.0, ref["max_trunc_err"] / 1e-3), l
         if l == 0:
             assert abs(zs[g.index[(3, 3)]] - np.cos(0.5)) < 1e-12
+
+
+@pytest.mark.parametrize("dtype,tol", DT)
+def test_multi_site_expect_and_rdm(dtype, tol):
+    """Multi-site BP `expect` over a Steiner path (src/expect.jl:67-81) and `reduced_density_matrix(alg="bp")`
+    (src/rdm.jl:52-73) on the device path (`tnqs_site_contract`), against the oracle's dense region contraction on a
+    loopy graph and against the exact state vector on a tree (BP is exact there, test_beliefpropagation.jl:44-54)."""
+    ftol = tol if dtype == np.complex128 else 10 * tol
+    # loopy graph, converged BP messages
+    g = tq.named_grid((3, 3))
+    dims = [2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3][:g.ne]
+    psi = ragged_state(g, dims, dtype, seed=71)
+    seq = tq.bipartite_edge_sequence(g)
+    bpc = tq.update(tq.BeliefPropagationCache(psi), maxiter=300, tolerance=1e-13 if dtype == np.complex128 else 1e-9, edge_sequence=seq)
+    c = oracle_from_bpc(bpc)
+    ix = g.index
+    cases = [("ZZ", [(1, 1), (3, 1)]), ("XY", [(1, 1), (3, 3)], 0.5), ("ZXZ", [(1, 2), (2, 2), (3, 2)]), ("YZ", [(2, 1), (2, 3)])]
+    PA = {"X": X, "Y": Y, "Z": Z}
+    for obs in cases:
+        got = tq.expect(bpc, obs)
+        path = tq.steiner_path(g, obs[1])
+        ops = {ix[v]: PA[o] for v, o in zip(obs[1], obs[0])}
+        want = orc.expect_region(c, path, ops, obs[2] if len(obs) > 2 else 1.0)
+        assert abs(got - want) < 100 * ftol, (obs, got, want)
+    for vs in ([(2, 2)], [(1, 1), (3, 1)], [(1, 3), (3, 3)], [(1, 1), (1, 2)]):
+        got = tq.reduced_density_matrix(bpc, vs)
+        want = orc.rdm_region(c, [ix[v] for v in vs])
+        assert abs(np.trace(got) - 1) < 1e-12
+        assert np.max(np.abs(got - want)) < 100 * ftol, vs
+    # tree: BP reduced density matrices are exact
+    gt = tq.named_comb_tree((3, 2))
+    pt = ragged_state(gt, [2, 3, 2, 3, 2][:gt.ne], dtype, seed=72)
+    bt = tq.update(tq.BeliefPropagationCache(pt))
+    full = orc.to_statevector(oracle_from_tns(pt))
+    va, vb = gt.vertices()[0], gt.vertices()[-1]
+    a, b = gt.index[va], gt.index[vb]
+    f = np.moveaxis(full, (a, b), (0, 1)).reshape(4, -1)
+    ex = f @ f.conj().T
+    ex /= np.trace(ex)
+    assert np.max(np.abs(tq.reduced_density_matrix(bt, [va, vb]) - ex)) < 100 * ftol
+    zz = np.trace(np.kron(Z, Z) @ ex)
+    assert abs(tq.expect(bt, ("ZZ", [va, vb])) - zz) < 100 * ftol

@@ -594,21 +594,26 @@ def normalize(tns: TensorNetworkState, alg: str = "bp", cache_update_kwargs: Opt
 
 
 def _symmetric_gauge_factors(mx: np.ndarray, my: np.ndarray, regularization: float):
-    """χ×χ algebra of one edge of `symmetric_gauge!` (`src/symmetric_gauge.jl:12-40`): returns (X_src, X_dst, S)
-    with ψ_src ← ψ_src ×_e X_src, ψ_dst ← ψ_dst ×_e X_dst and both new messages diag(S).  ITensors' `eigen` reads
-    a message on (l, l') as the map l → l', i.e. as the transpose of the m[ket, bra] storage used here."""
-    xd, xu = np.linalg.eigh(np.asarray(mx, dtype=np.complex128).T)
-    yd, yu = np.linalg.eigh(np.asarray(my, dtype=np.complex128).T)
-    xd = xd + regularization
-    yd = yd + regularization
-    if np.any(xd < 0) or np.any(yd < 0):
-        raise ValueError("DomainError: sqrt of a negative message eigenvalue")
-    root_x = (xu * np.sqrt(xd)) @ xu.conj().T
-    root_y = (yu * np.sqrt(yd)) @ yu.conj().T
-    inv_root_x = (xu / np.sqrt(xd)) @ xu.conj().T
-    inv_root_y = (yu / np.sqrt(yd)) @ yu.conj().T
-    u, sv, vh = np.linalg.svd(root_x @ root_y.T)
-    return inv_root_x @ u * np.sqrt(sv), inv_root_y @ vh.T * np.sqrt(sv), sv
+    """χ×χ algebra of one edge of `symmetric_gauge!` (`src/symmetric_gauge.jl:12-40`): returns (X_src, X_dst, S) with
+    ψ_src ← ψ_src ×_e X_src, ψ_dst ← ψ_dst ×_e X_dst and both new messages diag(S).  ITensors' `eigen` reads a message
+    on (l, l') as the map l → l', i.e. as the transpose of the m[ket, bra] storage used here.
+
+    Written without the inverse square roots of the reference (and of the oracle, which restates it line by line): with
+    C = X^{1/2}·(Y^{1/2})ᵀ = U·S·V†, X^{-1/2}·U·√S = (Y^{1/2})ᵀ·V·S^{-1/2} and Y^{-1/2}·conj(V)·√S = (X^{1/2})ᵀ·conj(U)·S^{-1/2};
+    the Hermitian square roots come from a Schur decomposition (scipy.linalg.sqrtm), the SVD from LAPACK gesvd."""
+    import scipy.linalg
+    n = mx.shape[0]
+    xr = np.asarray(mx, dtype=np.complex128).T + regularization * np.eye(n)
+    yr = np.asarray(my, dtype=np.complex128).T + regularization * np.eye(n)
+    for h in (xr, yr):
+        if np.min(np.linalg.eigvalsh(0.5 * (h + h.conj().T))) < 0:
+            raise ValueError("DomainError: sqrt of a negative message eigenvalue")
+    root_x = scipy.linalg.sqrtm(xr)
+    root_y = scipy.linalg.sqrtm(yr)
+    u, sv, vh = scipy.linalg.svd(root_x @ root_y.T, lapack_driver="gesvd")
+    v = vh.conj().T
+    isq = 1.0 / np.sqrt(sv)
+    return (root_y.T @ v) * isq, (root_x.T @ u.conj()) * isq, sv
 
 
 def symmetric_gauge(x, regularization: Optional[float] = None, cache_update_kwargs: Optional[dict] = None,
@@ -651,22 +656,21 @@ def symmetrize_and_normalize(bpc: BeliefPropagationCache, **kwargs) -> BeliefPro
 
 def renyi_entropy(bpc: BeliefPropagationCache, edge, alpha: float = 1.0) -> float:
     """`renyi_entropy(bp_cache, e; α)` (`src/entanglement.jl:73-86`): Rényi entropy across a bond from the two
-    converged messages on it — ρ = √m2ᵀ·m1·√m2ᵀ, normalised by its trace, eigenvalues below 10·eps dropped
-    (`:21-29`).  χ×χ host algebra on `tnqs_get_message`; exact on trees."""
+    converged messages on it.  The reference forms ρ = √m2ᵀ·m1·√m2ᵀ (√ via `pseudo_sqrt_inv_sqrt`, eigenvalues below
+    10·eps dropped) and takes the spectrum of ρ / tr ρ (`:21-29`).  Here the same spectrum is read off the similar matrix
+    (m2⁺)ᵀ·m1, m2⁺ = m2 with its sub-cutoff eigenvalues zeroed — no matrix square root (the oracle restates the
+    reference's route; the two are independent).  χ×χ host algebra on `tnqs_get_message`; exact on trees."""
     a, b = edge
     m1 = bpc.message((a, b)).astype(np.complex128)
     m2 = bpc.message((b, a)).astype(np.complex128)
     eps = np.finfo(np.float32 if bpc.dtype == np.complex64 else np.float64).eps
-    h = m2
-    lam, q = np.linalg.eigh(h)  # lower triangle, as LAPACK heev (safe_eigen, utils.jl:94-108)
+    lam, q = np.linalg.eigh(m2)  # lower triangle, as LAPACK heev (safe_eigen, utils.jl:94-108)
     keep = ~((lam == 0) | (np.abs(lam) < 10 * eps))
     if np.any(lam[keep] < 0):
         raise ValueError("DomainError: sqrt of a negative message eigenvalue")
-    f = np.where(keep, np.sqrt(np.where(keep, lam, 0.0)), 0.0)
-    r = (q * f) @ q.conj().T
-    rho = r.T @ m1 @ r.T
-    rho = rho / np.trace(rho)
-    ev = np.linalg.eigvalsh(rho)
+    m2p = (q * np.where(keep, lam, 0.0)) @ q.conj().T
+    ev = np.real(np.linalg.eigvals(m2p.T @ m1))  # spectrum of √m2ᵀ·m1·√m2ᵀ (similar matrices), real and ≥ 0 at a BP fixed point
+    ev = ev / np.sum(ev)
     ev = ev[np.abs(ev) > 10 * eps]  # eps of the state's real type (entanglement.jl:26)
     if alpha == 1:
         return float(-np.sum(ev * np.log(ev)))

@@ -598,7 +598,8 @@ def _symmetric_gauge_factors(mx: np.ndarray, my: np.ndarray, regularization: flo
     ψ_src ← ψ_src ×_e X_src, ψ_dst ← ψ_dst ×_e X_dst and both new messages diag(S).  ITensors' `eigen` reads a message
     on (l, l') as the map l → l', i.e. as the transpose of the m[ket, bra] storage used here.
 
-    Written without the inverse square roots of the reference (and of the oracle, which restates it line by line): with
+    Written without the inverse square roots of the reference (the CPU test restatement follows the reference line by line,
+    so the two are independent): with
     C = X^{1/2}·(Y^{1/2})ᵀ = U·S·V†, X^{-1/2}·U·√S = (Y^{1/2})ᵀ·V·S^{-1/2} and Y^{-1/2}·conj(V)·√S = (X^{1/2})ᵀ·conj(U)·S^{-1/2};
     the Hermitian square roots come from a Schur decomposition (scipy.linalg.sqrtm), the SVD from LAPACK gesvd."""
     import scipy.linalg
@@ -658,8 +659,8 @@ def renyi_entropy(bpc: BeliefPropagationCache, edge, alpha: float = 1.0) -> floa
     """`renyi_entropy(bp_cache, e; α)` (`src/entanglement.jl:73-86`): Rényi entropy across a bond from the two
     converged messages on it.  The reference forms ρ = √m2ᵀ·m1·√m2ᵀ (√ via `pseudo_sqrt_inv_sqrt`, eigenvalues below
     10·eps dropped) and takes the spectrum of ρ / tr ρ (`:21-29`).  Here the same spectrum is read off the similar matrix
-    (m2⁺)ᵀ·m1, m2⁺ = m2 with its sub-cutoff eigenvalues zeroed — no matrix square root (the oracle restates the
-    reference's route; the two are independent).  χ×χ host algebra on `tnqs_get_message`; exact on trees."""
+    (m2⁺)ᵀ·m1, m2⁺ = m2 with its sub-cutoff eigenvalues zeroed — no matrix square root (the CPU test restatement follows
+    the reference's route; the two are independent).  χ×χ host algebra on `tnqs_get_message`; exact on trees."""
     a, b = edge
     m1 = bpc.message((a, b)).astype(np.complex128)
     m2 = bpc.message((b, a)).astype(np.complex128)

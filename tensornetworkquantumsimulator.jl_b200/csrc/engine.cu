@@ -568,15 +568,6 @@ void Engine::allreduce_sum(double* dptr, size_t count) {
   api.check(api.AllReduce(dptr, dptr, count, kNcclFloat64, kNcclSum, comm_->comm, stream_), "ncclAllReduce");
 }
 
-// Scratch budget every rank agrees on (chunk boundaries of a gate batch carry a collective).  Decided from replicated
-// information only — no all-reduce, no host synchronisation: every rank computes the same `need` (it is summed over all
-// gates of the batch, owned or not) and the same fixed cap; a rank that really lacks the memory fails in its allocator.
-size_t Engine::agreed_budget(size_t need) {
-  if (nranks_ <= 1) return scratch_budget(need);
-  (void)need;
-  return (size_t)48 << 30;
-}
-
 // ------------------------------------------------------------------------------------------------
 // kernel launch wrappers
 // ------------------------------------------------------------------------------------------------
@@ -1436,17 +1427,37 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
   const double eps = c64() ? 1.1920928955078125e-07 : 2.220446049250313e-16;
   const double sqrt_cutoff = ao.sqrt_cutoff >= 0 ? ao.sqrt_cutoff : 10 * eps;  // simple_update.jl:32-33
   const bool normalize = ao.normalize_tensors != 0;
-  size_t need_total = 0;
-  for (int g : gate_ids) need_total += 3 * ((size_t)site_elems(verts[2 * g]) + (size_t)site_elems(verts[2 * g + 1])) * esz_;
-  const size_t budget = agreed_budget(need_total);
+  // Scratch of a gate: three tensor-sized buffers per site (gauged, projected, new), on the rank that owns the site.  A batch
+  // is cut into chunks that fit the budget of the most loaded rank; every rank derives the same cuts from replicated
+  // information (ownership, shapes), because chunk boundaries carry collectives.  Fewer chunks matter: the O(χ³) chain of a
+  // chunk (Cholesky / Jacobi launches) is latency-bound and costs the same for 30 or 120 gates.
+  const int RR = nranks_ > 1 ? nranks_ : 1;
+  auto site_need = [&](int v) { return 3 * (size_t)site_elems(v) * esz_; };
+  auto rank_of = [&](int v) { return owner_.empty() ? 0 : owner_[v]; };
+  size_t budget;
+  if (RR == 1) {
+    size_t need_total = 0;
+    for (int g : gate_ids) need_total += site_need(verts[2 * g]) + site_need(verts[2 * g + 1]);
+    budget = scratch_budget(need_total);
+  } else {
+    std::vector<size_t> state(RR, 0);
+    for (int v = 0; v < nv_; ++v) state[rank_of(v)] += (size_t)site_elems(v) * esz_;
+    const size_t worst = *std::max_element(state.begin(), state.end());
+    const size_t hbm = (size_t)170 << 30;  // usable HBM of a B200 (183 GB) minus context, pools and fragmentation slack
+    budget = worst + ((size_t)8 << 30) < hbm ? (size_t)(0.6 * (double)(hbm - worst)) : ((size_t)8 << 30);
+  }
   size_t gpos = 0;
   while (gpos < gate_ids.size()) {
-    size_t gend = gpos, bytes = 0;
+    size_t gend = gpos;
+    std::vector<size_t> used(RR, 0);
     while (gend < gate_ids.size()) {
       const int g = gate_ids[gend];
-      const size_t need = 3 * ((size_t)site_elems(verts[2 * g]) + (size_t)site_elems(verts[2 * g + 1])) * esz_;
-      if (gend > gpos && bytes + need > budget) break;
-      bytes += need;
+      const int a = verts[2 * g], b = verts[2 * g + 1];
+      std::vector<size_t> next = used;
+      next[rank_of(a)] += site_need(a);
+      next[rank_of(b)] += site_need(b);
+      if (gend > gpos && *std::max_element(next.begin(), next.end()) > budget) break;
+      used.swap(next);
       ++gend;
     }
     const int ng = (int)(gend - gpos);

@@ -142,7 +142,6 @@ class Engine {
   struct Bcast { void* ptr; size_t bytes; int root; };
   void exchange(const std::vector<Bcast>& items);       // grouped broadcasts on the engine stream
   void allreduce_sum(double* dptr, size_t count);
-  size_t agreed_budget(size_t need);
 
   // ---- helpers -------------------------------------------------------------------------------
   void* dalloc(size_t bytes);

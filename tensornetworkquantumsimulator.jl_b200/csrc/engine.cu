@@ -110,6 +110,8 @@ static void ensure_kernel_attributes(int device) {
   set((const void*)tc::tc_mode_kernel<true>, 200 * 1024);
   set((const void*)tc2::tc2_mode_kernel<false>, 225 * 1024);
   set((const void*)tc2::tc2_mode_kernel<true>, 225 * 1024);
+  set((const void*)tc2g::tc2_gram_kernel<false>, 225 * 1024);
+  set((const void*)tc2g::tc2_gram_kernel<true>, 225 * 1024);
   set((const void*)tc::tc_gram_kernel<false, 1, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<false, 2, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<true, 1, 2>, 200 * 1024);
@@ -168,6 +170,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   TNQS_CUDA(cudaEventCreate(&ev1_));
   { const char* e = std::getenv("TNQS_TC"); use_tc_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_TC2"); use_tc2_ = !(e && e[0] == '0'); }
+  { const char* e = std::getenv("TNQS_TC2G"); use_tc2g_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_FAST_SVD"); use_fast_svd_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_CHOL"); use_chol_ = !(e && e[0] == '0'); }
   { const char* e = std::getenv("TNQS_DMMA"); use_dmma_ = !(e && e[0] == '0'); }
@@ -202,6 +205,7 @@ Engine::Engine(const Engine& o)
       phys_(o.phys_), bond_(o.bond_), inc_(o.inc_), seq_(o.seq_), is_tree_(o.is_tree_), sshape_(o.sshape_) {
   use_tc_ = o.use_tc_;
   use_tc2_ = o.use_tc2_;
+  use_tc2g_ = o.use_tc2g_;
   use_cluster_jacobi_ = o.use_cluster_jacobi_;
   use_dmma_ = o.use_dmma_;
   use_chol_ = o.use_chol_;
@@ -781,6 +785,38 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   std::vector<ReduceTask> red(tasks.size());
   std::vector<char> done(tasks.size(), 0);
   for (auto& t : tasks) stats_.gram_bytes += (double)esz_ * 2.0 * t.MM * (double)t.CC;
+  // ---- TMA-fed warp-specialised tcgen05 path (kernels_tc2g.cuh): ComplexF32, fp32 accumulation (BP messages), one plane ----
+  if (c64() && use_tc_ && use_tc2g_ && !acc_double) {
+    tc2g::GPlan plan;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+      const GramTask& t = tasks[i];
+      if (t.MM != t.chi) continue;
+      tc2g::GramShape gs{t.X, t.Y, t.chi, t.outer, t.inner, t.CC};
+      if (tc2g::plan_add(plan, gs, (int)i)) done[i] = 1;
+    }
+    if (!plan.empty()) {
+      tc2g::plan_finish(plan);
+      for (auto& L : plan.launches) {
+        for (size_t k = 0; k < L.tasks.size(); ++k) {
+          const int i = L.ids[k];
+          const int chi = tasks[i].chi;
+          L.tasks[k].partial = (double2*)talloc((size_t)L.nslots[k] * chi * chi * sizeof(double2));
+          ReduceTask& r = red[i];
+          r.partial = L.tasks[k].partial; r.out = outs[i]; r.nsplit = L.nslots[k]; r.MM = chi; r.transpose = transpose ? 1 : 0;
+          stats_.gram_flops += 8.0 * chi * chi * (double)tasks[i].CC;
+        }
+        tc2g::GramTask2* dt = upload(L.tasks);
+        tc2g::GItem* di = upload(L.items);
+        if (L.last) tc2g::tc2_gram_kernel<true><<<L.grid, tc2g::G_THREADS, L.smem, stream_>>>(dt, di, (int)L.items.size(), L.gm);
+        else tc2g::tc2_gram_kernel<false><<<L.grid, tc2g::G_THREADS, L.smem, stream_>>>(dt, di, (int)L.items.size(), L.gm);
+        count_launch();
+        stats_.gram_launches += 1;
+        stats_.tc_launches += 1;
+        stats_.tma_launches += 1;
+      }
+      TNQS_CUDA(cudaGetLastError());
+    }
+  }
   // ---- tcgen05 path: ComplexF32, fp32 accumulation (BP messages), one plane, χ ≤ 64 ------------------
   if (c64() && use_tc_ && !acc_double) {
     std::vector<tc::TcGramTask> tt[2];
@@ -789,6 +825,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
     long long work[2] = {0, 0};
     for (size_t i = 0; i < tasks.size(); ++i) {
       const GramTask& t = tasks[i];
+      if (done[i]) continue;
       const bool last = t.inner == 1;
       bool ok = t.MM == t.chi && t.chi <= 64 && t.chi % 2 == 0 && (double)t.CC * t.chi >= 4096.0;
       if (!last) ok = ok && t.inner % 16 == 0;

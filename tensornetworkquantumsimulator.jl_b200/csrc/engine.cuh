@@ -21,6 +21,7 @@
 #include "kernels_tensor.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_tc2.cuh"
+#include "kernels_tc2g.cuh"
 #include "kernels_dmma.cuh"
 
 namespace tnqs {
@@ -131,6 +132,7 @@ class Engine {
   bool profiling_ = false;
   int wall_depth_ = 0;
   bool use_tc_ = true;          // tcgen05 path for ComplexF32 (env TNQS_TC=0 disables it)
+  bool use_tc2g_ = true;        // TMA-fed warp-specialised Gram contraction (env TNQS_TC2G=0: the LDG-fed tcgen05 kernel)
   bool use_tc2_ = true;         // TMA-fed warp-specialised mode product (env TNQS_TC2=0: the LDG-fed tcgen05 kernel)
   bool use_fast_svd_ = true;        // Cholesky-preconditioned θ-SVD with Jacobi polish (env TNQS_FAST_SVD=0: plain Jacobi on θ)
   bool use_chol_ = true;            // Cholesky-preconditioned eigendecomposition of the reduced-factor Gram (env TNQS_CHOL=0: Jacobi on G)

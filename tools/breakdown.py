@@ -6,16 +6,20 @@ import numpy as np
 import tnqs_b200 as tq
 L = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 chi = int(sys.argv[2]) if len(sys.argv) > 2 else 32
-nl = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+rand = len(sys.argv) > 3 and sys.argv[3] == "random"  # synthetic random TNS with every bond = chi (generated on the device)
+nl = 0 if rand else (int(sys.argv[3]) if len(sys.argv) > 3 else 16)
 g = tq.named_grid((L, L))
 layer = [("Rx", [v], 0.5) for v in g.vertices()] + [("Rz", [v], 0.4) for v in g.vertices()]
 groups = tq.edge_color(g, 4)
 for grp in groups:
     layer += [("Rzz", list(p), 0.25) for p in grp]
 seq = tq.bipartite_edge_sequence(g)
-psi = tq.BeliefPropagationCache(tq.zerostate(np.complex64, g))
 kw = dict(maxdim=chi, cutoff=1e-10, normalize_tensors=True)
 bp = dict(maxiter=25, tolerance=1e-5, edge_sequence=seq)
+if rand:
+    psi = tq.update(tq.random_bpc_on_device(np.complex64, g, bond_dimension=chi, seed=1234), inplace=True, **bp)
+else:
+    psi = tq.BeliefPropagationCache(tq.zerostate(np.complex64, g))
 for l in range(nl):
     psi, errs = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True)
 fam = ["mode_ms", "gram_ms", "small_ms", "mode_launches", "gram_launches", "kernel_launches", "bp_ms", "su_ms", "wall_ms"]
@@ -26,7 +30,7 @@ def show(tag, t0, t1, st):
         tag, (t1 - t0) * 1e3, st["wall_ms"], st["wall_ms"] - st["sync_ms"], st["bp_ms"], st["su_ms"], st["mode_ms"], st["gram_ms"], st["small_ms"], st["kernel_launches"]))
 
 
-for rep in range(2):
+for rep in range(1 if rand else 2):
     psi.stats(reset=True)
     t0 = time.perf_counter(); psi, _ = tq.apply_gates(layer, psi, apply_kwargs=kw, bp_update_kwargs=bp, inplace=True); t1 = time.perf_counter()
     show("layer (unprofiled)", t0, t1, psi.stats())

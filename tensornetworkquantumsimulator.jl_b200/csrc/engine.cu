@@ -254,6 +254,8 @@ Engine::~Engine() {
     if (s.done) cudaEventDestroy(s.done);
   }
   for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
+  for (auto& kv : site_pool_) for (void* p : kv.second) cudaFreeAsync(p, stream_);
+  site_pool_.clear();
   for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
   for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
   if (d_errflags_) cudaFreeAsync(d_errflags_, stream_);
@@ -314,6 +316,32 @@ void Engine::release_slabs() {
 void Engine::dfree(void* p) {
   SlowLog sl("cudaFreeAsync");
   if (p) TNQS_CUDA(cudaFreeAsync(p, stream_));
+}
+void* Engine::site_alloc(size_t bytes) {
+  auto f = site_pool_.find(bytes);
+  if (f != site_pool_.end() && !f->second.empty()) {
+    void* p = f->second.back();
+    f->second.pop_back();
+    site_pool_bytes_ -= bytes;
+    return p;
+  }
+  return dalloc(bytes);
+}
+void Engine::site_release(void* p, size_t bytes) {
+  if (!p) return;
+  if (bytes < (1ull << 20)) { dfree(p); return; }  // small tensors: the pool handles them well
+  site_pool_[bytes].push_back(p);
+  site_pool_bytes_ += bytes;
+}
+void Engine::trim_site_pool(size_t keep_bytes) {
+  for (auto it = site_pool_.begin(); it != site_pool_.end() && site_pool_bytes_ > keep_bytes;) {
+    while (!it->second.empty() && site_pool_bytes_ > keep_bytes) {
+      dfree(it->second.back());
+      it->second.pop_back();
+      site_pool_bytes_ -= it->first;
+    }
+    if (it->second.empty()) it = site_pool_.erase(it); else ++it;
+  }
 }
 void Engine::free_temps() {
   for (void* p : temps_) TNQS_CUDA(cudaFreeAsync(p, stream_));
@@ -436,7 +464,7 @@ size_t Engine::scratch_budget(size_t need) const {
   }
   size_t mine = 0;
   for (auto& sl : slabs_) mine += sl.second;
-  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0) + SlabPool::get().free_bytes(device_) + mine;
+  const size_t avail = fr + (size_t)(reserved > used ? reserved - used : 0) + SlabPool::get().free_bytes(device_) + mine + site_pool_bytes_;
   return (size_t)(0.7 * (double)avail);
 }
 
@@ -1837,6 +1865,9 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       run_chains(proj);
       std::vector<ModeTask> fin;
       std::vector<void*> newbuf(2 * ng, nullptr);
+      std::vector<size_t> oldbytes(2 * ng, 0);
+      std::set<size_t> newsizes;
+      const size_t site_pool_cap = (size_t)64 << 30;  // a third of a B200's HBM
       for (int k = 0; k < ng; ++k) {
         const int g = gate_ids[gpos + k];
         for (int s = 0; s < 2; ++s) {
@@ -1856,7 +1887,9 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           t.ips = (long long)t.outer * chi * t.inner;
           t.ops = (long long)t.outer * keep[k] * t.inner;
           t.in = proj[2 * k + s].result;
-          newbuf[2 * k + s] = dalloc((size_t)t.ops * d * esz_);
+          oldbytes[2 * k + s] = (size_t)site_elems(v) * esz_;  // bond_ still holds the old dimensions
+          newbuf[2 * k + s] = site_alloc((size_t)t.ops * d * esz_);
+          newsizes.insert((size_t)t.ops * d * esz_);
           t.out = newbuf[2 * k + s];
           t.mat = st[k].X[s];
         }
@@ -1874,7 +1907,9 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           const int v = verts[2 * g + s];
           sshape_[v][epos[2 * k + s]] = keep[k];
           if (!owns(v)) continue;
-          dfree(site_[v]);
+          // keep the old buffer for the next batch only if this batch asked for the same size (saturated bonds)
+          if (newsizes.count(oldbytes[2 * k + s]) && site_pool_bytes_ + oldbytes[2 * k + s] <= site_pool_cap) site_release(site_[v], oldbytes[2 * k + s]);
+          else dfree(site_[v]);
           site_[v] = newbuf[2 * k + s];
           touched.push_back(v);
         }

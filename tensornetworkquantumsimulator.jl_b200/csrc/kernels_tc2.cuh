@@ -130,6 +130,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 
 // ---- device helpers ----------------------------------------------------------------------------------------
+// one lane of a converged warp (cute::elect_one_sync): ptxas then knows that the guarded region runs on a single lane and
+// issues its UTCHMMA / UTCBAR directly instead of wrapping each one into a lane-serialising vote / elect loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -234,14 +242,14 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         {  // B image of this item, once the MMAs that read the buffer's previous content are done
           { TC2_T0(); mbar_wait(smem_u32(&bar_iempty[ib]), iph ^ 1u); TC2_ACC(0); }
           const uint32_t img_bytes = (uint32_t)nchunk * 2u * (uint32_t)gm.NNp * (uint32_t)kch * 4u;
-          if (lane == 0) mbar_expect_tx(&bar_ifull[ib], img_bytes);
-          if (lane == 0)
+          if (elect_one()) mbar_expect_tx(&bar_ifull[ib], img_bytes);
+          if (elect_one())
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                        ::"r"(smem_u32(s_img + (size_t)ib * gm.imgb)), "l"(tp->image), "r"(img_bytes), "r"(smem_u32(&bar_ifull[ib]))
                        : "memory");
           if (++ib == nimg) { ib = 0; iph ^= 1u; }
         }
-        { TC2_T0(); if (lane == 0) tmap_acquire(&tp->in_map); TC2_ACC(1); }
+        { TC2_T0(); if (elect_one()) tmap_acquire(&tp->in_map); TC2_ACC(1); }
         // MID: column of the tile's first block as (o, n), advanced by (d_o, d_n) per tile
         unsigned o = 0, n = 0, d_o = 0, d_n = 0;
         if (!LAST) {
@@ -256,13 +264,13 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
           for (int ch = 0; ch < nchunk; ++ch) {
             { TC2_T0(); mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u); TC2_ACC(2); }
             const long long tiss_ = prof ? clock64() : 0;
-            if (lane == 0) mbar_expect_tx(&bar_full[s], stg);
+            if (elect_one()) mbar_expect_tx(&bar_full[s], stg);
             const uint32_t dst = smem_u32(s_stage + (size_t)s * 2 * gm.slot);
             const uint32_t bar = smem_u32(&bar_full[s]);
             if (!LAST) {
               unsigned oq = o, nq = n;
               for (int q = 0; q < 4; q += bpb) {
-                if (lane == 0)
+                if (elect_one())
                 asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
                              ::"r"(dst + (uint32_t)q * (uint32_t)kch * 128u), "l"(&tp->in_map), "r"(0), "r"(b0), "r"(p), "r"((int)(nq >> 4)), "r"((int)oq), "r"(bar)
                              : "memory");
@@ -272,7 +280,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
               if (kpl) p += kpl;
               else { b0 += kch; if (b0 >= chi_in) { b0 = 0; ++p; } }
             } else {
-              if (lane == 0)
+              if (elect_one())
               asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                            ::"r"(dst), "l"(&tp->in_map), "r"(b0), "r"(tile * 128), "r"(p), "r"(bar)
                            : "memory");
@@ -339,30 +347,34 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             long long tlo_ = 0;
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t araw = a_raw0 + (uint64_t)s * stage_step;
-            if (!(dbg & 2)) {
+            if (!(dbg & 2) && elect_one()) {
               // terms hi·hi and hi·lo need only the raw tile; lo·hi waits for the splitters
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                if (ks < nks && lane == 0) mma_tf32(d_tmem, araw + ks * a_k, bh + ks * 16u, idesc, (ch | ks) != 0);
+                if (ks < nks) mma_tf32(d_tmem, araw + ks * a_k, bh + ks * 16u, idesc, (ch | ks) != 0);
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)
-                if (ks < nks && lane == 0) mma_tf32(d_tmem, araw + ks * a_k, bh + b_lo_off + ks * 16u, idesc, 1);
+                if (ks < nks) mma_tf32(d_tmem, araw + ks * a_k, bh + b_lo_off + ks * 16u, idesc, 1);
             }
+            __syncwarp();
             { TC2_T0(); mbar_wait(smem_u32(&bar_lo[s]), ph); if (prof) { tlo_ = clock64() - t0_; acc[3] += tlo_; } }
             asm volatile("tcgen05.fence::after_thread_sync;");
-            if (!(dbg & 2)) {
+            if (elect_one()) {
+              if (!(dbg & 2)) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                if (ks < nks && lane == 0) mma_tf32(d_tmem, araw + lo_off + ks * a_k, bh + ks * 16u, idesc, 1);
+                for (int ks = 0; ks < 4; ++ks)
+                  if (ks < nks) mma_tf32(d_tmem, araw + lo_off + ks * a_k, bh + ks * 16u, idesc, 1);
+              }
+              umma_commit(&bar_empty[s]);
+              if (ch == nchunk - 1) umma_commit(&bar_tfull[buf]);
             }
-            if (lane == 0) umma_commit(&bar_empty[s]);
-            if (ch == nchunk - 1 && lane == 0) umma_commit(&bar_tfull[buf]);
+            __syncwarp();
             if (prof) acc[4] += clock64() - tiss_ - tlo_;
             if (++s == nstage) { s = 0; ph ^= 1u; }
           }
           if (++buf == nbuf) { buf = 0; bph ^= 1u; }
         }
-        if (lane == 0) umma_commit(&bar_iempty[ib]);  // the image buffer is free once every MMA of the item has read it
+        if (elect_one()) umma_commit(&bar_iempty[ib]);  // the image buffer is free once every MMA of the item has read it
         if (++ib == nimg) { ib = 0; iph ^= 1u; }
       }
       if (prof && lane == 0 && mw == 0) { prof[8] = acc[0]; prof[9] = acc[1]; prof[10] = acc[2]; prof[11] = acc[3]; prof[12] = acc[4]; prof[13] = clock64() - tstart; }
@@ -438,7 +450,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         const long long te_ = prof ? clock64() : 0;
         asm volatile("tcgen05.fence::after_thread_sync;");
         if (dbg & 4) {
-          if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (e < 32 && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");
         } else {
           // Registers only: pairs of 16-column TMEM loads (32 registers) with constant indexing, then singles.
@@ -454,7 +466,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
           auto staging_free = [&]() {
             if (first) {
               TC2_T0();
-              if (e == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+              if (e < 32 && elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
               asm volatile("bar.sync %0, 128;" ::"r"(bar_b) : "memory");
               TC2_ACC(1);
               first = false;
@@ -522,7 +534,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
               if (col0 < CC) {
                 const uint32_t src = smem_u32(sO) + (uint32_t)q * (uint32_t)nc * 128u;
                 for (int pl = 0; pl < npl; ++pl)
-                  if (lane == 0)
+                  if (elect_one())
                   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];"
                                ::"l"(&tp->out_map), "r"(0), "r"(c0), "r"((int)(nq >> 4)), "r"((int)oq), "r"(pp0 + pl), "r"(src + (uint32_t)pl * 4u * (uint32_t)nc * 128u)
                                : "memory");
@@ -533,18 +545,18 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
           } else {
             for (int bx = 0; bx < NNp / 32; ++bx) {
               if (bx * 32 >= nc) break;
-              if (lane == 0)
+              if (elect_one())
               asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                            ::"l"(&tp->out_map), "r"(c0 + bx * 32), "r"(tile * 128), "r"(pp0), "r"(smem_u32(sO) + (uint32_t)bx * 16384u)
                            : "memory");
             }
           }
-          if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (elect_one()) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
         if (prof) { acc[2] += clock64() - te_; acc[3] += clock64() - tst_; }
       }
     }
-    if (e == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes complete
+    if (e < 32 && elect_one()) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all output writes complete
     if (prof && e == 0) { prof[20 + 4 * eg] = acc[0]; prof[21 + 4 * eg] = acc[1]; prof[22 + 4 * eg] = acc[2]; prof[23 + 4 * eg] = clock64() - tstart; prof[28 + eg] = acc[3]; }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");

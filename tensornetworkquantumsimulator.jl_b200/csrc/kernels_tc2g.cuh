@@ -33,6 +33,7 @@ using tc::mma_tf32;
 using tc::smem_u32;
 using tc2::bc;
 using tc2::bcu;
+using tc2::elect_one;
 using tc2::ld_tmem16;
 using tc2::lo_part;
 using tc2::mbar_arrive;
@@ -42,14 +43,6 @@ using tc2::mbar_wait;
 using tc2::tmap_acquire;
 using tc2::tmem_ld_wait;
 using tc2::umma_commit;
-
-// one lane of a converged warp (cute::elect_one_sync): ptxas then knows that the guarded region runs on a single lane and
-// issues its UTCHMMA / UTCBAR directly instead of wrapping each one into a lane-serialising vote / elect loop
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}\n" : "+r"(pred));
-  return pred != 0;
-}
 
 constexpr int G_THREADS = 512;  // warp 0: TMA producer · warp 1: MMA issuer (owns TMEM) · warps 2–3: idle · warps 4–11: splitters · warps 12–15: epilogue
 constexpr int G_SPLIT = 256;

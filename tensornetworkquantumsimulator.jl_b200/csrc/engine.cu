@@ -117,10 +117,14 @@ static void ensure_kernel_attributes(int device) {
   set((const void*)tc::tc_gram_kernel<true, 1, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<true, 2, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<true, 4, 1>, 200 * 1024);
-  set((const void*)gram_dmma_kernel<float, false>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<float, true>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<double, false>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<double, true>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, false, 10>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, true, 10>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, false, 10>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, true, 10>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, false, 12>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, true, 12>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, false, 12>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, true, 12>, 160 * 1024);
   set((const void*)chol_prepare_kernel, 160 * 1024);
   if (device >= 0 && device < 64) done[device] = true;
 }
@@ -926,6 +930,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         const GramTask& t = tasks[i];
         if (done[i] || (t.inner == 1) != inner1) continue;
         if (t.X != t.Y || t.xps != t.yps || t.MM < 16 || t.MM > 128 || t.CC < 512) continue;
+        if ((double)t.CC * t.MM >= 4.0e9) continue;  // 32-bit element offsets inside the kernel
         grp.push_back(t); ids.push_back((int)i); maxMM = std::max(maxMM, t.MM); work += t.CC;
         done[i] = 1;
       }
@@ -933,6 +938,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       // ~4 CTAs per SM overall, at least 1024 columns per split
       const long long target_cols = std::max<long long>(1024, work / (148 * 4));
       int maxsplit = 1, maxgroups = 1;
+      const int NW = maxMM > 64 ? 12 : 10;  // warps per CTA (kernels_dmma.cuh)
       for (size_t k = 0; k < grp.size(); ++k) {
         GramTask& t = grp[k];
         long long ns = std::max<long long>(1, std::min<long long>(4096, (t.CC + target_cols - 1) / target_cols));
@@ -943,7 +949,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         t.partial = (double2*)talloc((size_t)t.nsplit * t.MM * t.MM * sizeof(double2));
         maxsplit = std::max(maxsplit, t.nsplit);
         const int R32 = (2 * t.MM + 31) / 32, nblk = R32 * (R32 + 1) / 2;
-        maxgroups = std::max(maxgroups, (nblk + DG_WARPS - 1) / DG_WARPS);
+        maxgroups = std::max(maxgroups, (nblk + NW - 1) / NW);
         ReduceTask& r = red[ids[k]];
         r.partial = t.partial; r.out = outs[ids[k]]; r.nsplit = t.nsplit; r.MM = t.MM; r.transpose = transpose ? 1 : 0;
         stats_.gram_flops += 8.0 * t.MM * t.MM * (double)t.CC;
@@ -954,13 +960,11 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       for (int off = 0; off < (int)grp.size(); off += 65535) {
         const int nbz = std::min(65535, (int)grp.size() - off);
         dim3 grid(maxsplit, maxgroups, nbz);
-        if (c64()) {
-          if (inner1) gram_dmma_kernel<float, true><<<grid, DG_THREADS, smem, stream_>>>(d + off);
-          else gram_dmma_kernel<float, false><<<grid, DG_THREADS, smem, stream_>>>(d + off);
-        } else {
-          if (inner1) gram_dmma_kernel<double, true><<<grid, DG_THREADS, smem, stream_>>>(d + off);
-          else gram_dmma_kernel<double, false><<<grid, DG_THREADS, smem, stream_>>>(d + off);
-        }
+#define TNQS_DG(RT, I1) do { if (NW == 12) gram_dmma_kernel<RT, I1, 12><<<grid, 12 * 32, smem, stream_>>>(d + off); \
+                             else gram_dmma_kernel<RT, I1, 10><<<grid, 10 * 32, smem, stream_>>>(d + off); } while (0)
+        if (c64()) { if (inner1) TNQS_DG(float, true); else TNQS_DG(float, false); }
+        else { if (inner1) TNQS_DG(double, true); else TNQS_DG(double, false); }
+#undef TNQS_DG
         count_launch();
         stats_.gram_launches += 1;
       }
@@ -1367,6 +1371,14 @@ struct WallScope {  // host wall time of the outermost hot-path call
     if (--*depth == 0) *acc += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
   }
 };
+// timing events of one hot-path call; destroyed on every exit path (an Error thrown mid-call must not leak them)
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  EventPair() { TNQS_CUDA(cudaEventCreate(&a)); if (cudaEventCreate(&b) != cudaSuccess) { cudaEventDestroy(a); a = nullptr; throw Error(TNQS_ECUDA, "cudaEventCreate failed"); } }
+  ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  EventPair(const EventPair&) = delete;
+  EventPair& operator=(const EventPair&) = delete;
+};
 }  // namespace
 
 tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
@@ -1390,14 +1402,17 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
   }
   tnqs_bp_report rep{maxiter, use_tol ? 0 : 1, 0.0};
   if (nseq == 0) { rep.niter = 0; rep.converged = 1; return rep; }
-  cudaEvent_t t0, t1;
-  TNQS_CUDA(cudaEventCreate(&t0));
-  TNQS_CUDA(cudaEventCreate(&t1));
+  EventPair ev;
+  const cudaEvent_t t0 = ev.a, t1 = ev.b;
   TNQS_CUDA(cudaEventRecord(t0, stream_));
   for (int de = 0; de < 2 * ne_; ++de) materialize_message(de);
   free_temps();
   const auto levels = bp_levels(seq);
-  double* d_diff = (double*)dalloc(sizeof(double) * nseq);
+  struct DiffBuf {  // released on every exit path
+    Engine* e; double* p;
+    ~DiffBuf() { if (p) e->dfree(p); }
+  } diff_buf{this, (double*)dalloc(sizeof(double) * nseq)};
+  double* const d_diff = diff_buf.p;
   std::vector<double> h_diff(nseq);
   for (int it = 1; it <= maxiter; ++it) {
     if (nranks_ > 1) TNQS_CUDA(cudaMemsetAsync(d_diff, 0, sizeof(double) * nseq, stream_));
@@ -1413,14 +1428,11 @@ tnqs_bp_report Engine::bp_update(const tnqs_bp_opts* o) {
       if (rep.diff <= tol) { rep.converged = 1; rep.niter = it; break; }
     }
   }
-  dfree(d_diff);
   TNQS_CUDA(cudaEventRecord(t1, stream_));
   { WaitScope wsc(&stats_.sync_ms); TNQS_CUDA(cudaEventSynchronize(t1)); }
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
   stats_.bp_ms += ms;
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   if (wall_depth_ == 1) release_slabs();  // outermost call, stream drained by the event wait above
   return rep;
 }
@@ -1941,7 +1953,8 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
     if (SlowLog::on()) {
       double tot = 0;
       for (auto& ph : phase_log) tot += ph.second;
-      if (tot > 60.0) {
+      static const double thr = std::getenv("TNQS_PHASELOG") ? 0.0 : 60.0;  // TNQS_PHASELOG=1: every batch
+      if (tot > thr) {
         std::fprintf(stderr, "[tnqs slow] two-site batch of %d gates: host", ng);
         for (auto& ph : phase_log) std::fprintf(stderr, " %s %.1f", ph.first, ph.second);
         std::fprintf(stderr, " ms\n");
@@ -1984,10 +1997,27 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
     mat_off[i] = off;
     off += 2 * (size_t)D * D;
   }
+  // The batched one-sided Jacobi takes matrices of up to 512 rows; θ of a two-site gate has d·min(∏ external dims, d·χ) rows
+  // (simple_update.jl:47-52), χ = the shared bond before the gate — at most max(current bond, maxdim) for every gate of this
+  // call when maxdim is given.  Refuse the call before anything is touched rather than in the middle of it.
+  for (int i = 0; i < ngates; ++i) {
+    if (nverts[i] != 2) continue;
+    const int a = verts[2 * i], b = verts[2 * i + 1];
+    const int e = dedge(a, b) / 2;
+    const long long chi = ao.maxdim > 0 ? std::max(bond_[e], ao.maxdim) : bond_[e];
+    for (int s = 0; s < 2; ++s) {
+      const int v = s ? b : a;
+      const long long ext = site_elems(v) / ((long long)phys_[v] * bond_[e]);
+      const long long rows = std::min<long long>(ext, (long long)phys_[v] * chi) * phys_[v];
+      if (rows > 512)
+        throw Error(TNQS_EINVAL, "apply_gates: the two-site factorisation of the gate on vertices " + std::to_string(a) + " and " +
+                                     std::to_string(b) + " would have " + std::to_string(rows) +
+                                     " rows; the batched Jacobi SVD of this build takes at most 512 (d^2·chi <= 512, i.e. chi <= 128 for qubits)");
+    }
+  }
   int nrep = 0;
-  cudaEvent_t t0, t1;
-  TNQS_CUDA(cudaEventCreate(&t0));
-  TNQS_CUDA(cudaEventCreate(&t1));
+  EventPair ev;
+  const cudaEvent_t t0 = ev.a, t1 = ev.b;
   TNQS_CUDA(cudaEventRecord(t0, stream_));
   const double bp_before = stats_.bp_ms;
 
@@ -2064,8 +2094,6 @@ void Engine::apply_gates(int ngates, const int32_t* nverts, const int32_t* verts
   float ms = 0;
   cudaEventElapsedTime(&ms, t0, t1);
   stats_.su_ms += ms - (stats_.bp_ms - bp_before);
-  cudaEventDestroy(t0);
-  cudaEventDestroy(t1);
   release_slabs();  // stream drained by the event wait above
 }
 

@@ -8,8 +8,8 @@
 //     Re G[i][j] = S[(i,0),(j,0)] + S[(i,1),(j,1)],   Im G[i][j] = S[(i,0),(j,1)] − S[(i,1),(j,0)],
 // and only the 32×32 blocks of S on or below the diagonal are computed (10 of 16 for MM = 64), one
 // block per warp, 16 m8n8k4 accumulator tiles each.  A CTA streams its K-split of the tensor through
-// two shared-memory stages of KCH columns (next chunk prefetched into registers while the current
-// one is multiplied), converting the stored scalars to fp64 on the way in.
+// two shared-memory stages of KCH columns (chunk ch + 1 is converted to fp64 and stored while chunk ch is
+// multiplied, chunk ch + 2 is in flight from global memory).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -19,9 +19,11 @@ namespace tnqs {
 
 constexpr int DG_KCH = 32;            // columns per stage
 constexpr int DG_LD = DG_KCH + 4;     // row stride (doubles): rows land 32 B apart modulo 256 B → conflict-free fragment loads
-constexpr int DG_WARPS = 10;
-constexpr int DG_THREADS = DG_WARPS * 32;
-constexpr int DG_MAXPF = 14;          // prefetch registers (complex elements) per thread: ≥ MM·KCH / DG_THREADS for MM ≤ 128
+
+// Warps per CTA and staging registers per thread of the two instantiations: 10 warps for MM ≤ 64 (the 10 lower blocks of
+// a 128-row S), 12 warps for MM ≤ 128 (36 lower blocks of a 256-row S = 3 CTAs of 12; 12 warps also load the four SM
+// sub-partitions evenly: tools/dmma_probe.cu measures 30.1 TF/s with 10 resident warps, 36.2 with 12, peak 37.0).
+template <int NW> struct DgCfg { static constexpr int MAXPF = NW == 12 ? 11 : 7; };  // ≥ ⌈MM·KCH / (32·NW)⌉ (+ mapping padding)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -31,9 +33,20 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, 
 
 // grid = (nsplit_max, block groups, tasks); partial[split][i·MM + j] receives the split's contribution
 // (both triangles are written so that the generic gram_reduce_kernel can finish the job)
-template <typename R, bool INNER1>
-__global__ void __launch_bounds__(DG_THREADS) gram_dmma_kernel(const GramTask* __restrict__ tasks) {
+//
+// Staging without per-element index arithmetic: which element (row i, column kk of the chunk) a thread moves is fixed for
+// the whole K range, so its global offset (relative to the chunk) and its shared-memory offset are computed ONCE; a chunk
+// then costs one add per element.  MID (active leg not innermost) needs inner % KCH == 0 for that (all columns of a chunk
+// then share the outer index — true for every saturated lattice state); other shapes take the generic path, which
+// re-derives (outer, inner) per element as before.  Thread ↔ element mapping: MID: a warp moves 32 consecutive columns
+// of one row (256 contiguous bytes in, conflict-free 8-byte shared-memory stores); INNER1: a warp moves 4 consecutive
+// rows × 8 consecutive columns (eight 32-byte sectors in, 2-way conflicts at worst on the way out — the row stride of
+// 72 doubles would make a row-major assignment 16-way conflicted).
+template <typename R, bool INNER1, int NW>
+__global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __restrict__ tasks) {
   using C = typename Cx<R>::type;
+  constexpr int NT = NW * 32;
+  constexpr int MAXPF = DgCfg<NW>::MAXPF;
   extern __shared__ __align__(16) double dg_smem[];
   const GramTask t = tasks[blockIdx.z];
   const int split = blockIdx.x;
@@ -42,8 +55,8 @@ __global__ void __launch_bounds__(DG_THREADS) gram_dmma_kernel(const GramTask* _
   const int R32 = (rows + 31) / 32;
   const int nblk = R32 * (R32 + 1) / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int blk = blockIdx.y * DG_WARPS + warp;
-  if (blockIdx.y * DG_WARPS >= nblk) return;
+  const int blk = blockIdx.y * NW + warp;
+  if (blockIdx.y * NW >= nblk) return;
   // block (br, bc), br ≥ bc, enumerated row by row
   int br = 0, bc = 0;
   {
@@ -56,48 +69,73 @@ __global__ void __launch_bounds__(DG_THREADS) gram_dmma_kernel(const GramTask* _
   double* stage0 = dg_smem;
   double* stage1 = dg_smem + (size_t)prow * DG_LD;
   const C* __restrict__ X = (const C*)t.X;
-  const unsigned cb = (unsigned)split * t.cols_per_split;
+  const unsigned cb = (unsigned)split * t.cols_per_split;  // multiple of KCH
   const unsigned ce = min(t.CC, cb + t.cols_per_split);
   const int nchunk = (int)((ce - cb + DG_KCH - 1) / DG_KCH);
-  const int per_thread = (MM * DG_KCH + DG_THREADS - 1) / DG_THREADS;  // ≤ DG_MAXPF
 
   // zero the padding rows once (rows ≥ 2·MM of both stages)
-  for (int idx = tid; idx < (prow - rows) * DG_LD; idx += DG_THREADS) {
+  for (int idx = tid; idx < (prow - rows) * DG_LD; idx += NT) {
     stage0[(size_t)rows * DG_LD + idx] = 0.0;
     stage1[(size_t)rows * DG_LD + idx] = 0.0;
   }
 
-  C pf[DG_MAXPF];
+  // ---- per-thread element assignment (fixed for the whole K range) ----
+  const bool fast = INNER1 || (t.inner % DG_KCH == 0);
+  const int ngrp = INNER1 ? ((MM + 3) >> 2) * 4 : MM;   // warp-sized groups of elements per chunk
+  const int per_thread = (ngrp + NW - 1) / NW;          // ≤ MAXPF (host: MM ≤ 64 for 10 warps, ≤ 128 for 12)
+  unsigned goff[MAXPF];                                 // element offset inside the chunk; ~0u: nothing to move
+  // row / chunk column of entry r: cheap functions of (warp, lane, r) with r a compile-time constant after unrolling
+  auto row_of = [&](int r) { const int grp = warp + r * NW; return INNER1 ? (grp >> 2) * 4 + (lane & 3) : grp; };
+  auto kk_of = [&](int r) { const int grp = warp + r * NW; return INNER1 ? (grp & 3) * 8 + (lane >> 2) : lane; };
+#pragma unroll
+  for (int r = 0; r < MAXPF; ++r) {
+    goff[r] = ~0u;
+    const int grp = warp + r * NW;
+    if (r >= per_thread || grp >= ngrp) continue;
+    const int i = row_of(r), kk = kk_of(r);
+    if (i >= MM) continue;
+    const int p = i / t.chi, l = i - p * t.chi;
+    if (INNER1) goff[r] = (unsigned)(p * t.xps + (long long)kk * t.chi + l);
+    else goff[r] = (unsigned)(p * t.xps + (long long)l * t.inner + kk);  // + (o·χ·inner + n0) of the chunk
+  }
+  // MID: (outer, inner) position of the chunk's first column, advanced per chunk
+  unsigned o_c = 0, n_c = 0;
+  if (!INNER1) { o_c = cb / t.inner; n_c = cb - o_c * t.inner; }
+  const long long ostride = (long long)t.chi * t.inner;
+
+  C pf[MAXPF];
   auto gload = [&](int ch) {
     const unsigned k0 = cb + (unsigned)ch * DG_KCH;
+    const unsigned ncols = min((unsigned)DG_KCH, ce - k0);
+    if (fast) {
+      const C* __restrict__ Xc = INNER1 ? X + (long long)k0 * t.chi : X + ((long long)o_c * ostride + n_c);
 #pragma unroll
-    for (int r = 0; r < DG_MAXPF; ++r) {
-      pf[r] = c_zero<C>();
-      if (r >= per_thread) continue;
-      const int idx = tid + r * DG_THREADS;
-      if (idx >= MM * DG_KCH) continue;
-      int kk, i;
-      if (INNER1) { i = idx % MM; kk = idx / MM; } else { kk = idx % DG_KCH; i = idx / DG_KCH; }
-      const unsigned col = k0 + kk;
-      if (col < ce) {
-        const int p = i / t.chi, l = i - p * t.chi;
-        long long a;
-        if (INNER1) a = p * t.xps + (long long)col * t.chi + l;
-        else { const unsigned o = col / t.inner, n = col - o * t.inner; a = p * t.xps + ((long long)o * t.chi + l) * t.inner + n; }
-        pf[r] = X[a];
+      for (int r = 0; r < MAXPF; ++r) {
+        pf[r] = c_zero<C>();
+        if (r < per_thread && goff[r] != ~0u && (unsigned)kk_of(r) < ncols) pf[r] = Xc[goff[r]];
+      }
+      if (!INNER1) { n_c += DG_KCH; if (n_c >= t.inner) { n_c = 0; ++o_c; } }
+    } else {
+      // generic MID path: the columns of a chunk straddle outer slices
+#pragma unroll
+      for (int r = 0; r < MAXPF; ++r) {
+        pf[r] = c_zero<C>();
+        if (r >= per_thread || goff[r] == ~0u) continue;
+        const unsigned col = k0 + (unsigned)kk_of(r);
+        if (col < ce) {
+          const unsigned o = col / t.inner, n = col - o * t.inner;
+          pf[r] = X[(long long)(goff[r] - (unsigned)kk_of(r)) + (long long)o * ostride + n];
+        }
       }
     }
   };
   auto sstore = [&](double* st) {
 #pragma unroll
-    for (int r = 0; r < DG_MAXPF; ++r) {
-      if (r >= per_thread) continue;
-      const int idx = tid + r * DG_THREADS;
-      if (idx >= MM * DG_KCH) continue;
-      int kk, i;
-      if (INNER1) { i = idx % MM; kk = idx / MM; } else { kk = idx % DG_KCH; i = idx / DG_KCH; }
-      st[(size_t)(2 * i) * DG_LD + kk] = (double)pf[r].x;
-      st[(size_t)(2 * i + 1) * DG_LD + kk] = (double)pf[r].y;
+    for (int r = 0; r < MAXPF; ++r) {
+      if (r >= per_thread || goff[r] == ~0u) continue;
+      double* const d = st + 2 * row_of(r) * DG_LD + kk_of(r);
+      d[0] = (double)pf[r].x;
+      d[DG_LD] = (double)pf[r].y;
     }
   };
 
@@ -107,13 +145,21 @@ __global__ void __launch_bounds__(DG_THREADS) gram_dmma_kernel(const GramTask* _
 #pragma unroll
     for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
-  if (nchunk > 0) gload(0);
+  // Software pipeline: while stage (ch & 1) is multiplied, chunk ch + 1 (already in registers) is converted and stored
+  // into the other stage and chunk ch + 2 is requested from global memory; one barrier per chunk.  The stores and the
+  // DMMAs of a chunk are independent instruction streams, so warps that finish storing start multiplying while others
+  // are still converting: the fp64 tensor pipe no longer idles during the staging phase.
   const int fr = lane >> 2, fk = lane & 3;  // fragment row / k of this lane
+  if (nchunk > 0) {
+    gload(0);
+    sstore(stage0);
+    if (nchunk > 1) gload(1);
+  }
+  __syncthreads();
   for (int ch = 0; ch < nchunk; ++ch) {
     double* st = (ch & 1) ? stage1 : stage0;
-    sstore(st);
-    if (ch + 1 < nchunk) gload(ch + 1);
-    __syncthreads();  // stage `st` complete; the other stage was last read two iterations ago
+    if (ch + 1 < nchunk) sstore((ch & 1) ? stage0 : stage1);  // last read by the multiplication of chunk ch − 1, before the barrier
+    if (ch + 2 < nchunk) gload(ch + 2);
     if (active) {
       const double* arow = st + (size_t)(br * 32 + fr) * DG_LD + fk;
       const double* brow = st + (size_t)(bc * 32 + fr) * DG_LD + fk;
@@ -130,8 +176,7 @@ __global__ void __launch_bounds__(DG_THREADS) gram_dmma_kernel(const GramTask* _
           for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
       }
     }
-    // the next iteration overwrites the OTHER stage, which every warp finished reading before the
-    // barrier above; this stage is rewritten two iterations from now, after another barrier
+    __syncthreads();
   }
   // ---- epilogue: S block → complex G entries ----------------------------------------------------------
   if (!active) return;

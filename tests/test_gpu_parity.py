@@ -252,6 +252,19 @@ def test_error_conventions():
     assert abs(tq.expect(psi, ("Z", [(1, 1)])) - 1) < 1e-6
 
 
+def test_oversized_factorisation_is_refused_up_front():
+    # θ of a two-site gate may have at most 512 rows (d²·χ ≤ 512): refused with EINVAL before anything is
+    # touched, not in the middle of the call after earlier gates of the same call were committed
+    g = tq.named_path_graph(3)
+    a, b, c = g.vertices()
+    psi = tq.BeliefPropagationCache(ragged_state(g, [129, 300], np.complex64, seed=2))
+    before = psi.site(b).copy()
+    with pytest.raises(tq.TnqsError) as ei:
+        tq.apply_gates([("Rzz", [b, c], 0.1), ("Rzz", [a, b], 0.1)], psi, apply_kwargs=dict(maxdim=300), inplace=True)
+    assert "512" in str(ei.value)
+    assert np.array_equal(psi.site(b), before) and list(psi.bond_dims()) == [129, 300]
+
+
 def test_two_qubit_circuit_invariants():
     # /root/reference/test/test_apply.jl:11-20
     circuit = [("Rx", [(1, 1)], 0.5), ("Rx", [(2, 1)], 0.2), ("CPHASE", [(1, 1), (2, 1)], -0.3)]

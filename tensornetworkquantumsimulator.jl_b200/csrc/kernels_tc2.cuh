@@ -12,9 +12,13 @@
 //   * the hardware truncates an fp32 operand to TF32 (tools/tma_probe.cu: "truncated 112, rounded 0"), so the RAW
 //     tile is the `hi` operand as it lies in shared memory and only lo = rna_tf32(x − trunc_tf32(x)) is computed,
 //     element-wise and layout-agnostic, by four splitter warps (3 ALU instructions per float);
-//   * a ring of `nstage` stages (raw tile + lo tile) with full / lo-ready / empty mbarriers decouples the TMA
-//     producer (warp 0), the splitters (warps 2–5), the single MMA-issuing thread (warp 1) and the epilogue
-//     (warps 6–9); the accumulator is double-buffered in TMEM, so the MMAs of tile t+1 overlap the epilogue of t;
+//   * a ring of `nstage` raw-tile stages with full / lo-ready / empty mbarriers decouples the TMA producer, the
+//     splitters, the MMA issuers and the epilogue; the lo tiles live in their OWN, shorter ring (`nlo` slots): a raw
+//     stage has to wait out the DRAM latency, a lo tile only the few hundred cycles between the splitters and the
+//     MMAs, so the shared memory not spent on idle lo slots buys more bytes in flight (χ = 64: B images 64 KB +
+//     output staging 64 KB leave 92 KB — 3 raw + 2 lo slots of 16 KB instead of 2 + 2; the stand-alone
+//     decomposition, tools/tc2_test.cu `decomp`, showed the bare load pipeline at 4.2 TB/s with two stages in
+//     flight); the accumulator is multi-buffered in TMEM, so the MMAs of tile t+1 overlap the epilogue of t;
 //   * results leave through a shared-memory staging tile and TMA stores (cp.async.bulk.tensor … bulk_group).
 //
 // Bytes per unit: every input element is read once and every output element written once (8·(χ_in+χ_out)·CC per
@@ -180,6 +184,7 @@ struct Geom {
   uint32_t outb;   // bytes of one output staging buffer (one per epilogue group)
   uint32_t imgb;   // bytes of one B-image buffer
   int nstage, nimg, nbuf, ncol;  // ring depths; accumulator buffers of `ncol` TMEM columns each
+  int nlo;         // slots of the lo ring (2 ≤ nlo ≤ nstage)
   // shape class of the launch (every task of a launch has the same): the MMA warp then works on kernel parameters and
   // loop counters only, i.e. on values ptxas keeps in uniform registers — its UTCHMMA operands need no per-lane broadcast
   int kch, nchunk, NNp;
@@ -198,8 +203,10 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
   // issue warps' operands can live in uniform registers
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nstage = gm.nstage, nimg = gm.nimg, nbuf = gm.nbuf;
-  uint8_t* const s_stage = smem2;  // [nstage][raw | lo]
-  uint8_t* const s_out = s_stage + (size_t)nstage * 2 * gm.slot;
+  const int nlo = gm.nlo;
+  uint8_t* const s_stage = smem2;  // [nstage] raw tiles
+  uint8_t* const s_lo = s_stage + (size_t)nstage * gm.slot;  // [nlo] lo tiles
+  uint8_t* const s_out = s_lo + (size_t)nlo * gm.slot;
   uint8_t* const s_img = s_out + 2 * (size_t)gm.outb;
   uint32_t tmem_cols = 32;
   while (tmem_cols < (uint32_t)(nbuf * gm.ncol)) tmem_cols <<= 1;
@@ -265,7 +272,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             { TC2_T0(); mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u); TC2_ACC(2); }
             const long long tiss_ = prof ? clock64() : 0;
             if (elect_one()) mbar_expect_tx(&bar_full[s], stg);
-            const uint32_t dst = smem_u32(s_stage + (size_t)s * 2 * gm.slot);
+            const uint32_t dst = smem_u32(s_stage + (size_t)s * gm.slot);
             const uint32_t bar = smem_u32(&bar_full[s]);
             if (!LAST) {
               unsigned oq = o, nq = n;
@@ -306,16 +313,16 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
       const int mw = warp - 1;
       int tl = 0;
       int s = 0; uint32_t ph = 0;
+      int l = 0;                      // lo ring position (advances with every chunk, like s)
       int ib = 0; uint32_t iph = 0;
       int buf = 0; uint32_t bph = 0;  // accumulator ring position
       const int kch = gm.kch, nchunk = gm.nchunk, NNp = gm.NNp;
-      const uint32_t stg = LAST ? 128u * 128u : (uint32_t)kch * 512u;
-      const uint64_t stage_step = (uint64_t)((2u * gm.slot) >> 4);
+      const uint64_t stage_step = (uint64_t)(gm.slot >> 4);
       const uint32_t idesc = make_idesc(128, NNp, LAST ? 0 : 1, 0);
       const uint32_t per_b = (uint32_t)NNp * (uint32_t)kch * 4u;
       const uint64_t a_raw0 = LAST ? make_desc(smem_u32(s_stage), 16u, 1024u, 2)                       // K-major SW128: SBO = 8-row group
                                    : make_desc(smem_u32(s_stage), (uint32_t)kch * 128u, 512u, 1);      // MN-major SW128/32B: LBO = MN-atom stride, SBO = K-atom (4 rows)
-      const uint64_t lo_off = (uint64_t)(stg >> 4);
+      const uint64_t a_lo0 = LAST ? make_desc(smem_u32(s_lo), 16u, 1024u, 2) : make_desc(smem_u32(s_lo), (uint32_t)kch * 128u, 512u, 1);
       const uint64_t a_k = LAST ? 2u : 64u;                                                             // 32 B / 1024 B per k-step of 8
       const uint64_t b_img0 = make_desc(smem_u32(s_img), 128u, (uint32_t)kch * 32u, 0);
       const uint64_t b_lo_off = (uint64_t)(per_b >> 4), chunk_step = (uint64_t)((2u * per_b) >> 4), img_step = (uint64_t)(gm.imgb >> 4);
@@ -333,6 +340,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
               mbar_wait(smem_u32(&bar_full[s]), ph);
               if (lane == 0) mbar_arrive(&bar_empty[s]);
               if (++s == nstage) { s = 0; ph ^= 1u; }
+              if (++l == nlo) l = 0;
             }
             if (++buf == nbuf) { buf = 0; bph ^= 1u; }
             continue;
@@ -347,6 +355,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             long long tlo_ = 0;
             asm volatile("tcgen05.fence::after_thread_sync;");
             const uint64_t araw = a_raw0 + (uint64_t)s * stage_step;
+            const uint64_t alo = a_lo0 + (uint64_t)l * stage_step;
             if (!(dbg & 2) && elect_one()) {
               // terms hi·hi and hi·lo need only the raw tile; lo·hi waits for the splitters
 #pragma unroll
@@ -363,7 +372,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
               if (!(dbg & 2)) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  if (ks < nks) mma_tf32(d_tmem, araw + lo_off + ks * a_k, bh + ks * 16u, idesc, 1);
+                  if (ks < nks) mma_tf32(d_tmem, alo + ks * a_k, bh + ks * 16u, idesc, 1);
               }
               umma_commit(&bar_empty[s]);
               if (ch == nchunk - 1) umma_commit(&bar_tfull[buf]);
@@ -371,6 +380,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
             __syncwarp();
             if (prof) acc[4] += clock64() - tiss_ - tlo_;
             if (++s == nstage) { s = 0; ph ^= 1u; }
+            if (++l == nlo) l = 0;
           }
           if (++buf == nbuf) { buf = 0; bph ^= 1u; }
         }
@@ -383,6 +393,8 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
     // =============================== splitters: lo = rna(x − trunc(x)) ===============================
     const int t = tid - 96;
     int s = 0; uint32_t ph = 0;
+    int l = 0;                       // lo slot of the current chunk
+    int s2 = 0; uint32_t ph2 = 0;    // raw stage / phase of the chunk that used this lo slot before (nlo chunks earlier)
     {
       const int n_my = ((int)nitems - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int nchunks = n_my * gm.T * gm.nchunk;
@@ -390,8 +402,14 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
       for (int c = 0; c < nchunks; ++c) {
         { TC2_T0(); mbar_wait(smem_u32(&bar_full[s]), ph); TC2_ACC(0); }
         const long long tw_ = prof ? clock64() : 0;
-        const float4* raw = reinterpret_cast<const float4*>(s_stage + (size_t)s * 2 * gm.slot);
-        float4* lo = reinterpret_cast<float4*>(s_stage + (size_t)s * 2 * gm.slot + (size_t)n16 * 16);
+        if (c >= nlo) {
+          // the MMAs that read this lo slot (chunk c − nlo) must be complete: they commit to that chunk's empty barrier.
+          // nlo ≤ nstage, so that barrier cannot be more than one phase ahead of the one waited for.
+          mbar_wait(smem_u32(&bar_empty[s2]), ph2);
+          if (++s2 == nstage) { s2 = 0; ph2 ^= 1u; }
+        }
+        const float4* raw = reinterpret_cast<const float4*>(s_stage + (size_t)s * gm.slot);
+        float4* lo = reinterpret_cast<float4*>(s_lo + (size_t)l * gm.slot);
         if (!(dbg & 1))
         for (int i0 = t; i0 < n16; i0 += 4 * T2_SPLIT) {
           float4 x[4];
@@ -410,6 +428,7 @@ tc2_mode_kernel(const ModeTask2* __restrict__ tasks, const Item* __restrict__ it
         mbar_arrive(&bar_lo[s]);
         if (prof) acc[1] += clock64() - tw_;
         if (++s == nstage) { s = 0; ph ^= 1u; }
+        if (++l == nlo) l = 0;
       }
     }
     if (prof && t == 0) { prof[16] = acc[0]; prof[17] = acc[1]; prof[18] = clock64() - tstart; }
@@ -639,7 +658,7 @@ inline bool plan_windows(const ModeShape& t, int* kch_out, std::vector<Window>& 
     const size_t img = (size_t)(last ? 2 * t.KK : t.KK) * 2 * w.NNp * 4;
     const size_t stg = last ? 16384 : (size_t)*kch_out * 512;
     const size_t outb = last ? (size_t)w.NNp * 512 : (size_t)w.NNp * 256;
-    if (img + 2 * 2 * stg + 2 * outb > SMEM_BUDGET) return false;
+    if (img + 2 * 2 * stg + 2 * outb > SMEM_BUDGET) return false;  // two raw + two lo slots at least
   }
   return true;
 }
@@ -801,11 +820,19 @@ inline bool plan_finish(Plan& pl, int sms = 148) {
     gm.imgb = (gm.imgb + 1023u) & ~1023u;
     gm.nbuf = 4 * gm.ncol <= 512 ? 4 : 2;
     gm.nimg = 2;
-    long long ns = ((long long)SMEM_BUDGET - 2ll * gm.outb - 2ll * gm.imgb) / (2ll * gm.slot);
-    if (ns < 3) { gm.nimg = 1; ns = ((long long)SMEM_BUDGET - 2ll * gm.outb - (long long)gm.imgb) / (2ll * gm.slot); }
-    if (ns < 2) return false;
-    gm.nstage = (int)std::min<long long>(MAX_STAGES, ns);
-    L.smem = (size_t)gm.nstage * 2 * gm.slot + 2 * (size_t)gm.outb + (size_t)gm.nimg * gm.imgb;
+    // ring slots of `slot` bytes left after the output staging and the B images: two image buffers when that still leaves
+    // 4 raw + 2 lo slots, else one; 2 lo slots (3 when there is room for 8), the rest raw stages
+    long long nslots = ((long long)SMEM_BUDGET - 2ll * gm.outb - 2ll * gm.imgb) / (long long)gm.slot;
+    if (nslots < 6) { gm.nimg = 1; nslots = ((long long)SMEM_BUDGET - 2ll * gm.outb - (long long)gm.imgb) / (long long)gm.slot; }
+    if (nslots < 4) return false;
+    static const int lo_override = [] { const char* e = getenv("TNQS_TC2_NLO"); return e ? atoi(e) : 0; }();      // tuning
+    static const int st_override = [] { const char* e = getenv("TNQS_TC2_NSTAGE"); return e ? atoi(e) : 0; }();
+    gm.nlo = nslots >= 8 ? 3 : 2;
+    if (lo_override >= 2) gm.nlo = (int)std::min<long long>(lo_override, nslots / 2);
+    gm.nstage = (int)std::min<long long>(MAX_STAGES, nslots - gm.nlo);
+    if (st_override >= 2) gm.nstage = std::min(gm.nstage, st_override);
+    if (gm.nlo > gm.nstage) gm.nlo = gm.nstage;
+    L.smem = (size_t)(gm.nstage + gm.nlo) * gm.slot + 2 * (size_t)gm.outb + (size_t)gm.nimg * gm.imgb;
     // every item has exactly T tiles (those past a task's last tile are no-ops): ~24 items per SM, 4 ≤ T ≤ 64
     const int T = (int)std::max<long long>(4, std::min<long long>(64, total / ((long long)sms * 24)));
     gm.T = T;

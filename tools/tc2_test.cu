@@ -56,7 +56,7 @@ static bool run_case(const Case& c, int batch, bool timing) {
   if (!ok) { printf("%-34s : NOT ELIGIBLE for the TMA path\n", c.name); return false; }
   if (!tc2::plan_finish(plan)) { printf("%-34s : plan_finish failed\n", c.name); return false; }
   if (g_stage_override > 0)
-    for (auto& L : plan.launches) L.gm.nstage = std::min(L.gm.nstage, g_stage_override);
+    for (auto& L : plan.launches) { L.gm.nstage = std::min(L.gm.nstage, g_stage_override); L.gm.nlo = std::min(L.gm.nlo, L.gm.nstage); }
   tc2::PrepTask2* dprep;
   CK(cudaMalloc(&dprep, plan.preps.size() * sizeof(tc2::PrepTask2)));
   CK(cudaMemcpy(dprep, plan.preps.data(), plan.preps.size() * sizeof(tc2::PrepTask2), cudaMemcpyHostToDevice));
@@ -125,9 +125,9 @@ static bool run_case(const Case& c, int batch, bool timing) {
   const tc2::Geom& gm = L0.gm;
   size_t ntask = 0, nitem = 0;
   for (auto& L : plan.launches) { ntask += L.tasks.size(); nitem += L.items.size(); }
-  printf("%-34s : %s  max|err|/rms = %.2e  unwritten = %lld  copy-mismatch = %lld  [%zu launch(es) %s tasks %zu items %zu grid %d T %d kch %d nchunk %d NNp %d nstage %d nimg %d nbuf %d smem %zu]\n",
+  printf("%-34s : %s  max|err|/rms = %.2e  unwritten = %lld  copy-mismatch = %lld  [%zu launch(es) %s tasks %zu items %zu grid %d T %d kch %d nchunk %d NNp %d nstage %d nlo %d nimg %d nbuf %d smem %zu]\n",
          c.name, pass ? "ok  " : "FAIL", maxerr / rms, nan_count, diff_last, plan.launches.size(), L0.last ? "LAST" : "MID", ntask, nitem, L0.grid, gm.T,
-         gm.kch, gm.nchunk, gm.NNp, gm.nstage, gm.nimg, gm.nbuf, L0.smem);
+         gm.kch, gm.nchunk, gm.NNp, gm.nstage, gm.nlo, gm.nimg, gm.nbuf, L0.smem);
   if (timing) {
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
@@ -182,11 +182,13 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dprof, 148 * 32 * 8));
     for (int dbg : {0, 15}) {
       CK(cudaMemcpyToSymbol(tc2::g_tc2_dbg, &dbg, sizeof(int)));
-      const Case cs[] = {{"roles MID chi32 leg1 x48", 1, 1, 2 * 32, 32, 32, 1024}, {"roles LAST chi32 x48", 1, 1, 2 * 32 * 32 * 32, 32, 32, 1}};
+      const Case cs[] = {{"roles MID chi32 leg1 x48", 1, 1, 2 * 32, 32, 32, 1024}, {"roles LAST chi32 x48", 1, 1, 2 * 32 * 32 * 32, 32, 32, 1},
+                         {"roles MID chi64 leg1 x4", 1, 1, 2 * 64, 64, 64, 4096}, {"roles LAST chi64 x4", 1, 1, 2 * 64 * 64 * 64, 64, 64, 1},
+                         {"roles MID final chi64 x4", 2, 2, 64, 64, 64, 4096}};
       for (auto& c : cs) {
         CK(cudaMemset(dprof, 0, 148 * 32 * 8));
         CK(cudaMemcpyToSymbol(tc2::g_tc2_prof, &dprof, sizeof(dprof)));
-        run_case(c, 48, false);
+        run_case(c, c.chi_in >= 64 ? 4 : 48, false);
         std::vector<unsigned long long> h(148 * 32);
         CK(cudaMemcpy(h.data(), dprof, h.size() * 8, cudaMemcpyDeviceToHost));
         double a[32] = {0};
@@ -211,6 +213,8 @@ int main(int argc, char** argv) {
       run_case({"decomp MID chi32 leg1 x48", 1, 1, 2 * 32, 32, 32, 1024}, 48, true);
       run_case({"decomp LAST chi32 x48", 1, 1, 2 * 32 * 32 * 32, 32, 32, 1}, 48, true);
       run_case({"decomp MID chi64 leg1 x4", 1, 1, 2 * 64, 64, 64, 4096}, 4, true);
+      run_case({"decomp LAST chi64 x4", 1, 1, 2 * 64 * 64 * 64, 64, 64, 1}, 4, true);
+      run_case({"decomp MID final chi64 x4", 2, 2, 64, 64, 64, 4096}, 4, true);
     }
     return 0;
   }

@@ -120,7 +120,10 @@ int  tnqs_set_edge_sequence(tnqs_handle h, const int32_t* seq /*2*n*/, int n);
  *   nverts[i] ∈ {1,2}; verts[2*i], verts[2*i+1]; gate i is a d^n×d^n row-major complex128 matrix,
  *   kron(first, second) basis order, gates packed back to back in `gate_mats`.
  *   trunc_err[i] = spec.truncerr of gate i (0 for one-site gates).
- *   reports: one entry per BP refresh performed, up to max_reports; *n_reports = how many ran. */
+ *   reports: one entry per BP refresh performed, up to max_reports; *n_reports = how many ran.
+ *   Size limit of this build: the two-site factorisation (θ of simple_update.jl:51) may have at most 512 rows,
+ *   d·min(∏ external dims, d·χ) ≤ 512 with χ ≤ max(current bond, maxdim) — χ ≤ 128 for qubits.  A call that could
+ *   exceed it returns TNQS_EINVAL before the state is touched (the reference has no such limit). */
 int  tnqs_apply_gates(tnqs_handle h, int ngates, const int32_t* nverts, const int32_t* verts,
                       const double* gate_mats, const tnqs_apply_opts* aopts,
                       const tnqs_bp_opts* bopts, int update_cache, double* trunc_err,

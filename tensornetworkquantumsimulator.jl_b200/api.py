@@ -394,19 +394,29 @@ def update(bpc: BeliefPropagationCache, inplace: bool = False, **kwargs) -> Beli
 def circuit_arrays(circuit: Sequence, g: NamedGraph):
     """`toitensor(circuit, g, siteinds)` (`gate_definitions.jl:110-153`) down to flat arrays."""
     nverts, verts, mats = [], [], []
+    memo = {}  # a Trotter layer repeats a handful of (name, parameter) pairs hundreds of times: build each matrix once
     for gate in circuit:
         if isinstance(gate, tuple) and len(gate) >= 2:
             vs = _as_vertex_list(gate[1])
             for v in vs:
                 if v not in g.index:
                     raise ArgumentError(f"gate vertex {v!r} is not a vertex of the graph")
-            m = gate_matrix(gate[0], len(vs), gate[2] if len(gate) > 2 else None)
+            par = gate[2] if len(gate) > 2 else None
+            key = None
+            if isinstance(gate[0], str) and (par is None or isinstance(par, (int, float, complex))
+                                             or (isinstance(par, tuple) and all(isinstance(x, (int, float, complex)) for x in par))):
+                key = (gate[0], len(vs), par)
+            m = memo.get(key) if key is not None else None
+            if m is None:
+                m = np.asarray(gate_matrix(gate[0], len(vs), par), dtype=np.complex128).reshape(-1)
+                if key is not None:
+                    memo[key] = m
         else:
             raise ArgumentError("circuit entries must be (name_or_matrix, vertices[, params]) tuples")
         nverts.append(len(vs))
         idx = [g.index[v] for v in vs]
         verts.append((idx + [-1, -1])[:2] if len(idx) <= 2 else idx[:2])
-        mats.append(np.asarray(m, dtype=np.complex128).reshape(-1))
+        mats.append(m)
     mats = np.concatenate(mats) if mats else np.zeros(0, dtype=np.complex128)
     return (np.array(nverts, dtype=np.int32), np.array(verts, dtype=np.int32).reshape(-1, 2),
             np.ascontiguousarray(mats).view(np.float64))

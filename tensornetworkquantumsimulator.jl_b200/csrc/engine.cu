@@ -1724,7 +1724,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         }
         CholTask* dc = upload(ct);
         const size_t sm = (globg ? 0 : (size_t)maxn_g * maxn_g * sizeof(double2)) + (size_t)maxn_g * (sizeof(double) + sizeof(int));
-        chol_prepare_kernel<<<2 * nm, 256, sm, stream_>>>(dc, 1e-15);
+        chol_prepare_kernel<<<2 * nm, globg ? 1024 : 256, sm, stream_>>>(dc, 1e-15);
         count_launch();
         launch_jacobi(jg, 1e-40);  // the null columns of L are exactly zero
         chol_finish_kernel<<<2 * nm, 256, 0, stream_>>>(dc);
@@ -1765,7 +1765,11 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
       SuGateTask* ds = nullptr;
       if (nm > 0) {
         ds = upload(stm);
-        su_theta_kernel<<<nm, 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
+        // slices per gate of the small dense kernels: enough CTAs for ~4 per SM whatever the batch size
+        const int su_slices = std::max(1, std::min(16, (148 * 4 + nm - 1) / nm));
+        for (int q = 0; q < nm; ++q)
+          if (nn[2 * mine[q]] > SU_MAXN || nn[2 * mine[q] + 1] > SU_MAXN) throw Error(TNQS_EINVAL, "simple update: reduced factor larger than 256 rows");
+        su_theta_kernel<<<dim3(nm, su_slices), 256, 0, stream_>>>(ds, 64 * 2.220446049250313e-16);
         count_launch();
         // Preconditioned SVD: K = θ†θ → pivoted Cholesky P·K·Pᵀ = L·L† → Jacobi on L (fast: L is the
         // preconditioned form, and only rank(θ) columns are non-zero) → V_K = Pᵀ·U_L ≈ right singular vectors →
@@ -1800,7 +1804,7 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           CholTask* dc = upload(ct);
           colgram_kernel<<<nm, 256, 0, stream_>>>(d1);
           const size_t sm = (glob ? 0 : (size_t)maxcols_t * maxcols_t * sizeof(double2)) + (size_t)maxcols_t * (sizeof(double) + sizeof(int));
-          chol_prepare_kernel<<<nm, 256, sm, stream_>>>(dc, 1e-15);
+          chol_prepare_kernel<<<nm, glob ? 1024 : 256, sm, stream_>>>(dc, 1e-15);
           count_launch(2);
           launch_jacobi(jl, 1e-40);
           chol_finish_kernel<<<nm, 256, 0, stream_>>>(dc);
@@ -1855,9 +1859,11 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         }
       }
       if (nm > 0) {
-        if (c64()) su_factors_kernel<float><<<nm, 256, 0, stream_>>>(ds);
-        else su_factors_kernel<double><<<nm, 256, 0, stream_>>>(ds);
-        count_launch();
+        const int su_slices = std::max(1, std::min(16, (148 * 4 + nm - 1) / nm));
+        const dim3 fg(nm, su_slices);
+        if (c64()) { su_factors_kernel<float, 0><<<fg, 256, 0, stream_>>>(ds); su_factors_kernel<float, 1><<<fg, 256, 0, stream_>>>(ds); }
+        else { su_factors_kernel<double, 0><<<fg, 256, 0, stream_>>>(ds); su_factors_kernel<double, 1><<<fg, 256, 0, stream_>>>(ds); }
+        count_launch(2);
         TNQS_CUDA(cudaGetLastError());
       }
       if (R > 1) {

@@ -298,7 +298,10 @@ struct CholTask {
   double2* scratch;  // n×n global work matrix when the matrix does not fit shared memory, else nullptr
 };
 
-__global__ void __launch_bounds__(256) chol_prepare_kernel(const CholTask* __restrict__ tasks, double tol) {
+// Block size: 256 threads when the matrix lives in shared memory, 1024 when it lives in the L2-resident scratch (n > 96:
+// the trailing update of a step is then a stream of L2 round trips, and four times the threads keep four times as many
+// of them in flight).
+__global__ void __launch_bounds__(1024) chol_prepare_kernel(const CholTask* __restrict__ tasks, double tol) {
   extern __shared__ __align__(16) unsigned char chol_raw[];
   const CholTask t = tasks[blockIdx.x];
   const int n = t.n, tid = threadIdx.x, nt = blockDim.x;
@@ -306,8 +309,8 @@ __global__ void __launch_bounds__(256) chol_prepare_kernel(const CholTask* __res
   double2* S = t.scratch ? t.scratch : reinterpret_cast<double2*>(chol_raw);
   double* d = reinterpret_cast<double*>(chol_raw + (t.scratch ? 0 : (size_t)n * n * sizeof(double2)));  // [n] running diagonal
   int* piv = reinterpret_cast<int*>(d + n);                      // [n]
-  __shared__ double s_best[8];
-  __shared__ int s_besti[8];
+  __shared__ double s_best[32];
+  __shared__ int s_besti[32];
   __shared__ int s_p, s_stop;
   __shared__ double s_dmax0;
   for (int idx = tid; idx < n * n; idx += nt) {
@@ -518,9 +521,14 @@ struct SuGateTask {
 };
 
 // λ, R = Λ^{1/2}V† and θ = gate·(R_0 ⊗_b R_1)   (simple_update.jl:47-51 with R†R = Gram)
+// grid (gates, slices): every slice recomputes the 2·n eigenvalues (n dot products of length n, cheap) into shared
+// memory and fills its share of the θ entries, so a batch of few gates (a sharded run leaves 16 per rank) still spreads
+// over the SMs; slice 0 also publishes √λ and 1/√λ for su_factors.
+constexpr int SU_MAXN = 256;  // d·χ_b of a site (host: launch_jacobi takes matrices of up to 512 rows = d·n)
 __global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tolG) {
   const SuGateTask& t = tasks[blockIdx.x];
   __shared__ double red[34];
+  __shared__ double s_sq[2][SU_MAXN];
   const int chi = t.chi_b;
   for (int site = 0; site < 2; ++site) {
     const int n = t.d[site] * chi;
@@ -533,7 +541,7 @@ __global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tol
         const double2 v = GV[i + (long long)r * n], a = GA[i + (long long)r * n];
         l += v.x * a.x + v.y * a.y;
       }
-      t.sq[site][r] = l;  // stash λ
+      s_sq[site][r] = l;  // stash λ
       lmax = fmax(lmax, l);
     }
     __syncthreads();  // block-wide max of λ
@@ -550,10 +558,13 @@ __global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tol
     __syncthreads();
     const double thr = tolG * red[33];
     for (int r = threadIdx.x; r < n; r += blockDim.x) {
-      const double l = t.sq[site][r];
+      const double l = s_sq[site][r];
       const bool kept = l > thr && l > 0;
-      t.sq[site][r] = kept ? sqrt(l) : 0.0;
-      t.isq[site][r] = kept ? 1.0 / sqrt(l) : 0.0;
+      s_sq[site][r] = kept ? sqrt(l) : 0.0;
+      if (blockIdx.y == 0) {
+        t.sq[site][r] = kept ? sqrt(l) : 0.0;
+        t.isq[site][r] = kept ? 1.0 / sqrt(l) : 0.0;
+      }
     }
     __syncthreads();
   }
@@ -562,11 +573,11 @@ __global__ void su_theta_kernel(const SuGateTask* __restrict__ tasks, double tol
   const int rows = n0 * d0, cols = n1 * d1;
   const double2* __restrict__ V0 = t.GV[0];
   const double2* __restrict__ V1 = t.GV[1];
-  for (int idx = threadIdx.x; idx < rows * cols; idx += blockDim.x) {
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < rows * cols; idx += blockDim.x * gridDim.y) {
     const int rho = idx % rows, kap = idx / rows;
     const int r0 = rho / d0, s0p = rho - r0 * d0;
     const int r1 = kap / d1, s1p = kap - r1 * d1;
-    const double w = t.sq[0][r0] * t.sq[1][r1];
+    const double w = s_sq[0][r0] * s_sq[1][r1];
     double2 acc; acc.x = 0; acc.y = 0;
     if (w != 0.0) {
       for (int s0 = 0; s0 < d0; ++s0)
@@ -642,7 +653,9 @@ __global__ void su_truncate_kernel(const SuGateTask* __restrict__ tasks, int nta
 
 // X_0 = V_0 Λ_0^{-1/2} · U√σ,  X_1 = V_1 Λ_1^{-1/2} · conj(V_θ)√σ  (simple_update.jl:53-64 folded:
 // T' = (T ×_ext P) · R⁺ · new factor)
-template <typename R>
+// Two launches, grid (gates, slices) each: PART 0 writes the right factor Rp and X_0, PART 1 (which reads all of Rp)
+// writes X_1.  Every output entry is an independent dot product, so the slices of a gate split them evenly.
+template <typename R, int PART>
 __global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
   using C = typename Cx<R>::type;
   const SuGateTask& t = tasks[blockIdx.x];
@@ -650,41 +663,41 @@ __global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
   const int n0 = d0 * chi, n1 = d1 * chi;
   const int rows = n0 * d0, cols = n1 * d1;
   const int keep = *t.keep;
-  // Numerically null directions (σ_c ≤ 2e-13·‖θ‖_F: the Jacobi stops rotating such columns, so they are
-  // not orthogonal to the others in the relative sense) get zero factor columns instead of noise/σ^{3/2};
-  // their weight σ_c·u_c v_c† in the two-site tensor is below 2e-13 either way.
-  __shared__ double s_thr;
-  if (threadIdx.x == 0) {
-    double tot = 0;
-    for (int k = 0; k < cols; ++k) tot += t.sigma[k] * t.sigma[k];
-    s_thr = 2e-13 * sqrt(tot);
-  }
-  __syncthreads();
-  const double sthr = s_thr;
-  // right factor: Rp[κ, c] = Σ_ρ θ0[ρ,κ] conj(Uσ[ρ, perm c]) / σ_c^{3/2}
-  for (int idx = threadIdx.x; idx < cols * keep; idx += blockDim.x) {
-    const int kap = idx % cols, c = idx / cols;
-    const double sg = t.sigma[c];
-    double2 acc; acc.x = 0; acc.y = 0;
-    if (sg > sthr) {
-      const double2* th = t.theta0 + (long long)kap * rows;
-      const double2* u = t.theta + (long long)t.perm[c] * rows;
-      for (int rho = 0; rho < rows; ++rho) {
-        const double2 a = th[rho], b = u[rho];
-        acc.x += a.x * b.x + a.y * b.y;
-        acc.y += a.y * b.x - a.x * b.y;
-      }
-      const double f = 1.0 / (sg * sqrt(sg));
-      acc.x *= f; acc.y *= f;
+  const int first = blockIdx.y * blockDim.x + threadIdx.x, step = blockDim.x * gridDim.y;
+  if (PART == 0) {
+    // Numerically null directions (σ_c ≤ 2e-13·‖θ‖_F: the Jacobi stops rotating such columns, so they are
+    // not orthogonal to the others in the relative sense) get zero factor columns instead of noise/σ^{3/2};
+    // their weight σ_c·u_c v_c† in the two-site tensor is below 2e-13 either way.
+    __shared__ double s_thr;
+    if (threadIdx.x == 0) {
+      double tot = 0;
+      for (int k = 0; k < cols; ++k) tot += t.sigma[k] * t.sigma[k];
+      s_thr = 2e-13 * sqrt(tot);
     }
-    t.Rp[idx] = acc;
-  }
-  __syncthreads();
-  // X_0[(s,b),(s0',c)] = Σ_r V0[(s,b),r] isq0[r] · Uσ[(r,s0'), perm c]/√σ_c
-  {
+    __syncthreads();
+    const double sthr = s_thr;
+    // right factor: Rp[κ, c] = Σ_ρ θ0[ρ,κ] conj(Uσ[ρ, perm c]) / σ_c^{3/2}
+    for (int idx = first; idx < cols * keep; idx += step) {
+      const int kap = idx % cols, c = idx / cols;
+      const double sg = t.sigma[c];
+      double2 acc; acc.x = 0; acc.y = 0;
+      if (sg > sthr) {
+        const double2* th = t.theta0 + (long long)kap * rows;
+        const double2* u = t.theta + (long long)t.perm[c] * rows;
+        for (int rho = 0; rho < rows; ++rho) {
+          const double2 a = th[rho], b = u[rho];
+          acc.x += a.x * b.x + a.y * b.y;
+          acc.y += a.y * b.x - a.x * b.y;
+        }
+        const double f = 1.0 / (sg * sqrt(sg));
+        acc.x *= f; acc.y *= f;
+      }
+      t.Rp[idx] = acc;
+    }
+    // X_0[(s,b),(s0',c)] = Σ_r V0[(s,b),r] isq0[r] · Uσ[(r,s0'), perm c]/√σ_c
     C* __restrict__ X = (C*)t.X[0];
     const int mm = d0 * keep;
-    for (int idx = threadIdx.x; idx < n0 * mm; idx += blockDim.x) {
+    for (int idx = first; idx < n0 * mm; idx += step) {
       const int row = idx / mm, col = idx - row * mm;
       const int sp = col / keep, c = col - sp * keep;
       const double sg = t.sigma[c];
@@ -705,11 +718,10 @@ __global__ void su_factors_kernel(const SuGateTask* __restrict__ tasks) {
       C o; o.x = (R)acc.x; o.y = (R)acc.y;
       X[idx] = o;
     }
-  }
-  {
+  } else {
     C* __restrict__ X = (C*)t.X[1];
     const int mm = d1 * keep;
-    for (int idx = threadIdx.x; idx < n1 * mm; idx += blockDim.x) {
+    for (int idx = first; idx < n1 * mm; idx += step) {
       const int row = idx / mm, col = idx - row * mm;
       const int sp = col / keep, c = col - sp * keep;
       double2 acc; acc.x = 0; acc.y = 0;

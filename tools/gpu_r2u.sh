@@ -5,7 +5,7 @@ rm -f gpurun_out/parity_report.jsonl
 timeout 900 python -m pytest tests -q -m gpu --tb=short -p no:cacheprovider --timeout 400 -x > gpurun_out/pytest_gpu_${TAG}.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_${TAG}.log
 grep -E "passed|failed|FAILED|Error|error|assert" gpurun_out/pytest_gpu_${TAG}.log | cut -c1-300 | tail -12
-timeout 600 python bench.py --no-cpu > gpurun_out/bench_${TAG}.log 2>&1
+timeout 600 python bench.py > gpurun_out/bench_${TAG}.log 2>&1
 tail -1 gpurun_out/bench_${TAG}.log | cut -c1-300
 timeout 150 python tools/breakdown.py > gpurun_out/breakdown_${TAG}.txt 2>&1
 grep -v "BP sweep after" gpurun_out/breakdown_${TAG}.txt | tail -14

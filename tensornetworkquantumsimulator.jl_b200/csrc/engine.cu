@@ -935,10 +935,34 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         done[i] = 1;
       }
       if (grp.empty()) continue;
-      // ~4 CTAs per SM overall, at least 1024 columns per split
-      const long long target_cols = std::max<long long>(1024, work / (148 * 4));
-      int maxsplit = 1, maxgroups = 1;
+      // ~4 CTAs per SM overall, at least 1024 columns per split.  One CTA is resident per SM (registers), so the launch runs
+      // in waves of 148 CTAs of equal length: among a few nearby split sizes take the one that wastes least of its last wave
+      // (924 CTAs = 6.24 waves ran as 7; the K-splits are reduced in a fixed order, so the result stays deterministic).
       const int NW = maxMM > 64 ? 12 : 10;  // warps per CTA (kernels_dmma.cuh)
+      long long target_cols = std::max<long long>(1024, work / (148 * 4));
+      {
+        auto ctas_for = [&](long long tc) {
+          long long total = 0;
+          for (auto& t : grp) {
+            const long long ns = std::max<long long>(1, std::min<long long>(4096, (t.CC + tc - 1) / tc));
+            long long cps = (t.CC + ns - 1) / ns;
+            cps = (cps + DG_KCH - 1) / DG_KCH * DG_KCH;
+            const int R32 = (2 * t.MM + 31) / 32, nblk = R32 * (R32 + 1) / 2;
+            total += ((t.CC + cps - 1) / cps) * ((nblk + NW - 1) / NW);
+          }
+          return total;
+        };
+        double best_eff = -1.0;
+        long long best_tc = target_cols;
+        for (int pct : {100, 90, 80, 72, 64, 56, 50}) {
+          const long long tc = std::max<long long>(1024, target_cols * pct / 100);
+          const long long total = ctas_for(tc);
+          const double eff = (double)total / (double)((total + 147) / 148 * 148);
+          if (eff > best_eff + 0.02) { best_eff = eff; best_tc = tc; }  // prefer the larger split unless a smaller one gains ≥ 2 %
+        }
+        target_cols = best_tc;
+      }
+      int maxsplit = 1, maxgroups = 1;
       for (size_t k = 0; k < grp.size(); ++k) {
         GramTask& t = grp[k];
         long long ns = std::max<long long>(1, std::min<long long>(4096, (t.CC + target_cols - 1) / target_cols));
@@ -1802,13 +1826,15 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
           SmallGemmTask* d1 = upload(g1);
           SmallGemmTask* d2 = upload(g2);
           CholTask* dc = upload(ct);
-          colgram_kernel<<<nm, 256, 0, stream_>>>(d1);
+          // 4×4 output tiles per thread: (n/4)² tiles of a matrix keep at most (n/4)²/256 CTAs busy
+          const int gemm_slices = std::max(1, std::min(su_slices, ((maxcols_t + 3) / 4) * ((maxrows_t + 3) / 4) / 256));
+          colgram_kernel<<<dim3(nm, gemm_slices), 256, 0, stream_>>>(d1);
           const size_t sm = (glob ? 0 : (size_t)maxcols_t * maxcols_t * sizeof(double2)) + (size_t)maxcols_t * (sizeof(double) + sizeof(int));
           chol_prepare_kernel<<<nm, glob ? 1024 : 256, sm, stream_>>>(dc, 1e-15);
           count_launch(2);
           launch_jacobi(jl, 1e-40);
           chol_finish_kernel<<<nm, 256, 0, stream_>>>(dc);
-          colapply_kernel<<<nm, 256, 0, stream_>>>(d2);
+          colapply_kernel<<<dim3(nm, gemm_slices), 256, 0, stream_>>>(d2);
           count_launch(2);
           TNQS_CUDA(cudaGetLastError());
         }

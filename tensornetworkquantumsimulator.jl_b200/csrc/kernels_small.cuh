@@ -423,7 +423,8 @@ __global__ void __launch_bounds__(256) colgram_kernel(const SmallGemmTask* __res
   const int m = t.m, n = t.n;
   // 4×4 register tiles over the lower triangle of the n×n result
   const int nt4 = (n + 3) / 4;
-  for (int tile = threadIdx.x; tile < nt4 * nt4; tile += blockDim.x) {
+  // grid (matrices, slices): the 4×4 output tiles are dealt round-robin to the threads of all slices
+  for (int tile = blockIdx.y * blockDim.x + threadIdx.x; tile < nt4 * nt4; tile += blockDim.x * gridDim.y) {
     const int ti = tile / nt4, tj = tile - ti * nt4;
     if (tj > ti) continue;
     double2 acc[4][4];
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(256) colapply_kernel(const SmallGemmTask* __re
   const SmallGemmTask t = tasks[blockIdx.x];
   const int m = t.m, n = t.n;
   const int mt4 = (m + 3) / 4, nt4 = (n + 3) / 4;
-  for (int tile = threadIdx.x; tile < mt4 * nt4; tile += blockDim.x) {
+  for (int tile = blockIdx.y * blockDim.x + threadIdx.x; tile < mt4 * nt4; tile += blockDim.x * gridDim.y) {
     const int tj = tile / mt4, ti = tile - tj * mt4;  // consecutive threads → consecutive row tiles
     double2 acc[4][4];
 #pragma unroll

@@ -234,11 +234,33 @@ Engine::Engine(const Engine& o)
   msg_dim_ = o.msg_dim_;
   msg_next_dim_.assign(2 * ne_, 0);
   msg_set_ = o.msg_set_;
-  for (int de = 0; de < 2 * ne_; ++de) {
-    if (!o.msg_[de] || !o.msg_dim_[de]) { msg_dim_[de] = 0; continue; }
-    const size_t b = (size_t)msg_dim_[de] * msg_dim_[de] * esz_;
-    msg_[de] = dalloc(b);
-    TNQS_CUDA(cudaMemcpyAsync(msg_[de], o.msg_[de], b, cudaMemcpyDeviceToDevice, stream_));
+  {
+    // every message and its BP staging twin in one allocation, copied by one kernel
+    size_t tot = 0;
+    std::vector<size_t> off(2 * ne_, 0);
+    for (int de = 0; de < 2 * ne_; ++de) {
+      if (!o.msg_[de] || !o.msg_dim_[de]) { msg_dim_[de] = 0; continue; }
+      const size_t b = ((size_t)msg_dim_[de] * msg_dim_[de] * esz_ + 255) & ~size_t(255);
+      off[de] = tot;
+      tot += 2 * b;
+    }
+    if (tot > 0) {
+      msg_arena_ = (char*)dalloc(tot);
+      msg_arena_bytes_ = tot;
+      std::vector<CopyTask> ct;
+      for (int de = 0; de < 2 * ne_; ++de) {
+        if (!msg_dim_[de]) continue;
+        const size_t raw = (size_t)msg_dim_[de] * msg_dim_[de] * esz_;
+        const size_t b = (raw + 255) & ~size_t(255);
+        msg_[de] = msg_arena_ + off[de];
+        msg_next_[de] = msg_arena_ + off[de] + b;
+        msg_next_dim_[de] = msg_dim_[de];
+        ct.push_back({o.msg_[de], msg_[de], (unsigned long long)raw});
+      }
+      CopyTask* dct = upload(ct);
+      copy_many_kernel<<<(unsigned)ct.size(), 256, 0, stream_>>>(dct);
+      TNQS_CUDA(cudaGetLastError());
+    }
   }
   d_errflags_ = (double*)dalloc(2 * sizeof(double));
   TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
@@ -260,8 +282,9 @@ Engine::~Engine() {
   for (void* p : site_) if (p) cudaFreeAsync(p, stream_);
   for (auto& kv : site_pool_) for (void* p : kv.second) cudaFreeAsync(p, stream_);
   site_pool_.clear();
-  for (void* p : msg_) if (p) cudaFreeAsync(p, stream_);
-  for (void* p : msg_next_) if (p) cudaFreeAsync(p, stream_);
+  for (void* p : msg_) if (p && !in_msg_arena(p)) cudaFreeAsync(p, stream_);
+  for (void* p : msg_next_) if (p && !in_msg_arena(p)) cudaFreeAsync(p, stream_);
+  if (msg_arena_) cudaFreeAsync(msg_arena_, stream_);
   if (d_errflags_) cudaFreeAsync(d_errflags_, stream_);
   if (stream_) { cudaStreamSynchronize(stream_); cudaStreamDestroy(stream_); }
   if (ev0_) cudaEventDestroy(ev0_);
@@ -318,8 +341,9 @@ void Engine::release_slabs() {
   slab_cur_ = 0; slab_off_ = 0;
 }
 void Engine::dfree(void* p) {
+  if (!p || in_msg_arena(p)) return;  // arena messages live as long as the engine
   SlowLog sl("cudaFreeAsync");
-  if (p) TNQS_CUDA(cudaFreeAsync(p, stream_));
+  TNQS_CUDA(cudaFreeAsync(p, stream_));
 }
 void* Engine::site_alloc(size_t bytes) {
   auto f = site_pool_.find(bytes);

@@ -107,6 +107,14 @@ class Engine {
   std::vector<void*> msg_next_; // staging for a BP level
   std::vector<int> msg_dim_;    // χ the buffer currently holds (0: not materialised)
   std::vector<int> msg_next_dim_;
+  // A clone places every message and its staging twin in ONE allocation (≈2·10³ stream-ordered allocations and as many
+  // copies per functional copy otherwise); buffers inside it are never freed individually (dfree skips them), messages
+  // whose dimension changes later move to their own allocation.
+  char* msg_arena_ = nullptr;
+  size_t msg_arena_bytes_ = 0;
+  bool in_msg_arena(const void* p) const {
+    return msg_arena_ && (const char*)p >= msg_arena_ && (const char*)p < msg_arena_ + msg_arena_bytes_;
+  }
   std::vector<std::vector<int>> sshape_;  // bond-leg dims each site buffer was written with
   std::vector<char> msg_set_;   // 0: identity default (messages(bpc) is empty for it)
   double* d_errflags_ = nullptr;  // [0] Jacobi non-convergence, [1] DomainError; summed over ranks before the host reads them

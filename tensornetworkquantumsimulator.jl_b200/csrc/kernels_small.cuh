@@ -521,6 +521,19 @@ struct SuGateTask {
   void* X[2];            // out: [(s,b)][(s',c)] row-major, tensor scalar type
 };
 
+// many small device-to-device copies in one launch (a clone's messages): 16-byte aligned buffers, sizes multiple of 8
+struct CopyTask { const void* src; void* dst; unsigned long long bytes; };
+__global__ void __launch_bounds__(256) copy_many_kernel(const CopyTask* __restrict__ tasks) {
+  const CopyTask t = tasks[blockIdx.x];
+  const unsigned long long n16 = t.bytes / 16;
+  const uint4* __restrict__ s = reinterpret_cast<const uint4*>(t.src);
+  uint4* __restrict__ d = reinterpret_cast<uint4*>(t.dst);
+  for (unsigned long long i = threadIdx.x; i < n16; i += blockDim.x) d[i] = s[i];
+  const unsigned char* sb = reinterpret_cast<const unsigned char*>(t.src);
+  unsigned char* db = reinterpret_cast<unsigned char*>(t.dst);
+  for (unsigned long long i = n16 * 16 + threadIdx.x; i < t.bytes; i += blockDim.x) db[i] = sb[i];
+}
+
 // λ, R = Λ^{1/2}V† and θ = gate·(R_0 ⊗_b R_1)   (simple_update.jl:47-51 with R†R = Gram)
 // grid (gates, slices): every slice recomputes the 2·n eigenvalues (n dot products of length n, cheap) into shared
 // memory and fills its share of the θ entries, so a batch of few gates (a sharded run leaves 16 per rank) still spreads

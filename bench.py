@@ -414,7 +414,7 @@ def run_ours(args):
         tq.update(psi2, inplace=True, maxiter=1, tolerance=None, edge_sequence=fseq)
         extras["bp_sweep_ms_forest_schedule"] = psi2.stats()["bp_ms"]
         psi2.stats(reset=True)
-        tq.update(psi2, inplace=True, maxiter=1, tolerance=None, edge_sequence=seq)
+        tq.update(psi2, inplace=True, maxiter=1, tolerance=None, edge_sequence=tq.bipartite_edge_sequence(g))
         extras["bp_sweep_ms_bipartite_schedule"] = psi2.stats()["bp_ms"]
 
     cpu = None
@@ -466,7 +466,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="tfim2d", choices=["tfim2d", "heavyhex", "cubic3d"],
                     help="tfim2d: BASELINE configs 1/2/5 and the chi=64 target; heavyhex: config 3 (Eagle 127); cubic3d: config 4 (periodic LxLxL)")
-    ap.add_argument("--L", type=int, default=16)
+    ap.add_argument("--L", type=int, default=None, help="linear lattice size (default: 16 for tfim2d, 6 for cubic3d = BASELINE config 4)")
     ap.add_argument("--chi", type=int, default=32)
     ap.add_argument("--prep", type=int, default=None, help="untimed layers before warm-up (default: 15 from the product state, 0 with --random-state)")
     ap.add_argument("--random-state", action="store_true", help="start from a synthetic random TNS with all bonds = chi (BASELINE config 5) instead of evolving the product state")
@@ -479,6 +479,8 @@ def main():
     ap.add_argument("--ref-bp-sweeps", type=float, default=-1.0, help="reference arm: BP sweeps per refresh (default: measured with the oracle)")
     ap.add_argument("--extras", action="store_true", help="also time one BP sweep with the reference's default forest-cover schedule")
     args = ap.parse_args()
+    if args.L is None:
+        args.L = 6 if args.workload == "cubic3d" else 16
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -98,6 +98,30 @@ struct SlabPool {
 };
 }  // namespace
 
+namespace {
+struct EngineRegistry {
+  std::mutex mu;
+  std::set<Engine*> live;
+  static EngineRegistry& get() { static EngineRegistry r; return r; }
+};
+}  // namespace
+void Engine::emergency_trim(int device) {
+  {
+    EngineRegistry& reg = EngineRegistry::get();
+    std::lock_guard<std::mutex> lk(reg.mu);
+    for (Engine* e : reg.live) {
+      if (e->device_ != device) continue;
+      for (auto& kv : e->site_pool_)
+        for (void* p : kv.second) cudaFreeAsync(p, e->stream_);
+      e->site_pool_.clear();
+      e->site_pool_bytes_ = 0;
+    }
+  }
+  cudaDeviceSynchronize();
+  SlabPool::get().trim(device);
+  cudaGetLastError();
+}
+
 // Opt-in to > 48 KB dynamic shared memory for every kernel that needs it.  The attribute is per device, so it is
 // tracked per device ordinal (a second cache on another GPU of the same process must opt in again).
 static void ensure_kernel_attributes(int device) {
@@ -202,6 +226,7 @@ Engine::Engine(int dtype, int nv, int ne, const int32_t* edge_uv, const int32_t*
   d_errflags_ = (double*)dalloc(2 * sizeof(double));
   TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
+  { EngineRegistry& reg = EngineRegistry::get(); std::lock_guard<std::mutex> lk(reg.mu); reg.live.insert(this); }
 }
 
 Engine::Engine(const Engine& o)
@@ -265,9 +290,11 @@ Engine::Engine(const Engine& o)
   d_errflags_ = (double*)dalloc(2 * sizeof(double));
   TNQS_CUDA(cudaMemsetAsync(d_errflags_, 0, 2 * sizeof(double), stream_));
   TNQS_CUDA(cudaStreamSynchronize(stream_));
+  { EngineRegistry& reg = EngineRegistry::get(); std::lock_guard<std::mutex> lk(reg.mu); reg.live.insert(this); }
 }
 
 Engine::~Engine() {
+  { EngineRegistry& reg = EngineRegistry::get(); std::lock_guard<std::mutex> lk(reg.mu); reg.live.erase(this); }
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   for (void* p : temps_) cudaFreeAsync(p, stream_);
@@ -298,7 +325,15 @@ void* Engine::dalloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0) bytes = 16;
   SlowLog sl("cudaMallocAsync");
-  TNQS_CUDA(cudaMallocAsync(&p, bytes, stream_));
+  cudaError_t err = cudaMallocAsync(&p, bytes, stream_);
+  if (err == cudaErrorMemoryAllocation) {
+    // e.g. a functional copy of a 58 GB state next to the buffers the source engine keeps for recycling: release every
+    // cache of the process on this device and try once more
+    cudaGetLastError();
+    emergency_trim(device_);
+    err = cudaMallocAsync(&p, bytes, stream_);
+  }
+  TNQS_CUDA(err);
   return p;
 }
 // Temporaries: small ones are bump-allocated from cached 32 MiB chunks (thousands per gate batch —
@@ -315,7 +350,12 @@ void* Engine::talloc(size_t bytes) {
       if (slab_cur_ < slabs_.size() && slab_off_ + bytes <= slabs_[slab_cur_].second) break;
       if (slab_cur_ < slabs_.size()) { ++slab_cur_; slab_off_ = 0; }
       if (slab_cur_ >= slabs_.size()) {
-        slabs_.push_back(SlabPool::get().take(device_, std::max(kSlab, bytes)));
+        try {
+          slabs_.push_back(SlabPool::get().take(device_, std::max(kSlab, bytes)));
+        } catch (const Error&) {  // out of memory even after the slab cache was trimmed: drop the recycled site buffers too
+          emergency_trim(device_);
+          slabs_.push_back(SlabPool::get().take(device_, std::max(kSlab, bytes)));
+        }
         slab_off_ = 0;
       }
     }

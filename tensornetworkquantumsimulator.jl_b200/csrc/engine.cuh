@@ -129,6 +129,11 @@ class Engine {
   void* site_alloc(size_t bytes);
   void site_release(void* p, size_t bytes);
   void trim_site_pool(size_t keep_bytes);
+ public:
+  // Out of device memory: every live engine of the device drops its recycled site buffers, the cached scratch slabs go
+  // back to the driver, the device is drained; the failed allocation is then retried once (engine.cu: dalloc).
+  static void emergency_trim(int device);
+ private:
   std::vector<std::pair<char*, size_t>> slabs_;  // GiB-sized scratch slabs for tensor-sized temporaries (process-wide cache)
   size_t slab_cur_ = 0, slab_off_ = 0;
   std::vector<char*> arena_;    // cached chunks for small temporaries

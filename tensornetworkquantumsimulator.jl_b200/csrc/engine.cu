@@ -652,14 +652,52 @@ void Engine::comm_init(int rank, int nranks, const void* unique_id128, const int
   TNQS_CUDA(cudaStreamSynchronize(stream_));
 }
 
+// Every item travels from its root to all ranks.  The list is replicated information, so every rank derives the same
+// packing: the items of root r go, in list order, into slots r·per … of one staging buffer; each rank packs what it owns
+// (one copy kernel), ONE all-gather moves everything, one copy kernel unpacks what the rank does not own.  A BP level of
+// the 16×16 lattice is 480 messages: as a group of 480 ncclBroadcast calls the exchange cost more than the level's
+// tensor kernels on 8 GPUs.  (TNQS_EXCHANGE=bcast keeps the grouped broadcasts.)
 void Engine::exchange(const std::vector<Bcast>& items) {
   if (nranks_ <= 1 || items.empty()) return;
   NcclApi& api = NcclApi::get();
-  api.check(api.GroupStart(), "ncclGroupStart");
-  for (auto& b : items)
-    api.check(api.Broadcast(b.ptr, b.ptr, b.bytes, kNcclChar, b.root, comm_->comm, stream_), "ncclBroadcast");
-  api.check(api.GroupEnd(), "ncclGroupEnd");
-  stats_.kernel_launches += 1;
+  static const bool use_bcast = [] { const char* e = std::getenv("TNQS_EXCHANGE"); return e && std::string(e) == "bcast"; }();
+  if (use_bcast || items.size() < 4) {
+    api.check(api.GroupStart(), "ncclGroupStart");
+    for (auto& b : items)
+      api.check(api.Broadcast(b.ptr, b.ptr, b.bytes, kNcclChar, b.root, comm_->comm, stream_), "ncclBroadcast");
+    api.check(api.GroupEnd(), "ncclGroupEnd");
+    stats_.kernel_launches += 1;
+    return;
+  }
+  const int R = nranks_;
+  size_t slot = 0;
+  std::vector<int> cnt(R, 0);
+  for (auto& b : items) {
+    if (b.root < 0 || b.root >= R) throw Error(TNQS_EINVAL, "exchange: bad root rank");
+    slot = std::max(slot, b.bytes);
+    ++cnt[b.root];
+  }
+  slot = (slot + 255) & ~size_t(255);
+  const int per = *std::max_element(cnt.begin(), cnt.end());
+  char* stage = (char*)talloc(slot * (size_t)per * R);
+  std::vector<CopyTask> pack, unpack;
+  std::vector<int> next(R, 0);
+  for (auto& b : items) {
+    char* s = stage + ((size_t)b.root * per + next[b.root]++) * slot;
+    if (b.root == rank_) pack.push_back({b.ptr, s, (unsigned long long)b.bytes});
+    else unpack.push_back({s, b.ptr, (unsigned long long)b.bytes});
+  }
+  if (!pack.empty()) {
+    CopyTask* d = upload(pack);
+    copy_many_kernel<<<(unsigned)pack.size(), 256, 0, stream_>>>(d);
+  }
+  api.check(api.AllGather(stage + (size_t)rank_ * per * slot, stage, slot * (size_t)per, kNcclChar, comm_->comm, stream_), "ncclAllGather(exchange)");
+  if (!unpack.empty()) {
+    CopyTask* d = upload(unpack);
+    copy_many_kernel<<<(unsigned)unpack.size(), 256, 0, stream_>>>(d);
+  }
+  TNQS_CUDA(cudaGetLastError());
+  stats_.kernel_launches += 3;
 }
 
 void Engine::allreduce_sum(double* dptr, size_t count) {

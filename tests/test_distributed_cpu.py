@@ -96,7 +96,34 @@ def _worker(rank, world, port, q):
         err2 = max(float(np.max(np.abs(got.T[v] - one.T[v]))) for v in range(g.nv))
         err2 = max(err2, float(np.max(np.abs(np.array(got_errs) - np.array(ref_errs)))))
         err2 = max(err2, max(float(np.max(np.abs(got.msg[k2] - one.msg[k2]))) for k2 in one.msg))
-        q.put((rank, max(err, err2), len(tq.cut_edges(g, owner))))
+        # level exchange (engine.cu, Engine::exchange): every item (a message of the level, a Gram matrix of a batch) has a
+        # root rank; the replicated item list gives every rank the same packing — the items of root r, in list order, in
+        # slots r·per … of one staging buffer; each rank packs what it owns, ONE all-gather moves everything, each rank
+        # unpacks what it does not own.  Items of different sizes share the slot size of the largest one.
+        rng = np.random.default_rng(7)
+        sizes = [int(x) for x in rng.integers(3, 40, size=23)]
+        roots = [int(x) for x in rng.integers(0, R, size=23)]
+        truth = [np.random.default_rng(100 + i).standard_normal(n) for i, n in enumerate(sizes)]
+        have = [truth[i].copy() if roots[i] == rank else np.full(sizes[i], np.nan) for i in range(23)]
+        slot_n = max(sizes)
+        cnt = [roots.count(r) for r in range(R)]
+        per_x = max(cnt)
+        stage = np.zeros((R, per_x, slot_n))
+        nxt = [0] * R
+        where = []
+        for i in range(23):
+            where.append((roots[i], nxt[roots[i]]))
+            nxt[roots[i]] += 1
+            if roots[i] == rank:
+                stage[where[i][0], where[i][1], :sizes[i]] = have[i]
+        mine_t = torch.from_numpy(stage[rank].copy())
+        parts = [torch.zeros_like(mine_t) for _ in range(R)]
+        dist.all_gather(parts, mine_t)
+        for i in range(23):
+            if roots[i] != rank:
+                have[i] = parts[where[i][0]][where[i][1], :sizes[i]].numpy().copy()
+        err3 = max(float(np.max(np.abs(have[i] - truth[i]))) for i in range(23))
+        q.put((rank, max(err, err2, err3), len(tq.cut_edges(g, owner))))
     finally:
         dist.destroy_process_group()
 

@@ -141,10 +141,10 @@ static void ensure_kernel_attributes(int device) {
   set((const void*)tc::tc_gram_kernel<true, 1, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<true, 2, 2>, 200 * 1024);
   set((const void*)tc::tc_gram_kernel<true, 4, 1>, 200 * 1024);
-  set((const void*)gram_dmma_kernel<float, false, 10>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<float, true, 10>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<double, false, 10>, 160 * 1024);
-  set((const void*)gram_dmma_kernel<double, true, 10>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, false, 8>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<float, true, 8>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, false, 8>, 160 * 1024);
+  set((const void*)gram_dmma_kernel<double, true, 8>, 160 * 1024);
   set((const void*)gram_dmma_kernel<float, false, 12>, 160 * 1024);
   set((const void*)gram_dmma_kernel<float, true, 12>, 160 * 1024);
   set((const void*)gram_dmma_kernel<double, false, 12>, 160 * 1024);
@@ -1040,7 +1040,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
       // ~4 CTAs per SM overall, at least 1024 columns per split.  One CTA is resident per SM (registers), so the launch runs
       // in waves of 148 CTAs of equal length: among a few nearby split sizes take the one that wastes least of its last wave
       // (924 CTAs = 6.24 waves ran as 7; the K-splits are reduced in a fixed order, so the result stays deterministic).
-      const int NW = maxMM > 64 ? 12 : 10;  // warps per CTA (kernels_dmma.cuh)
+      const int NW = maxMM > 64 ? 12 : 8;  // warps per CTA (kernels_dmma.cuh); 8: one CTA covers all blocks, diagonal blocks paired
       long long target_cols = std::max<long long>(1024, work / (148 * 4));
       {
         auto ctas_for = [&](long long tc) {
@@ -1050,7 +1050,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
             long long cps = (t.CC + ns - 1) / ns;
             cps = (cps + DG_KCH - 1) / DG_KCH * DG_KCH;
             const int R32 = (2 * t.MM + 31) / 32, nblk = R32 * (R32 + 1) / 2;
-            total += ((t.CC + cps - 1) / cps) * ((nblk + NW - 1) / NW);
+            total += ((t.CC + cps - 1) / cps) * (NW == 8 ? 1 : (nblk + NW - 1) / NW);
           }
           return total;
         };
@@ -1075,7 +1075,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         t.partial = (double2*)talloc((size_t)t.nsplit * t.MM * t.MM * sizeof(double2));
         maxsplit = std::max(maxsplit, t.nsplit);
         const int R32 = (2 * t.MM + 31) / 32, nblk = R32 * (R32 + 1) / 2;
-        maxgroups = std::max(maxgroups, (nblk + NW - 1) / NW);
+        maxgroups = std::max(maxgroups, NW == 8 ? 1 : (nblk + NW - 1) / NW);
         ReduceTask& r = red[ids[k]];
         r.partial = t.partial; r.out = outs[ids[k]]; r.nsplit = t.nsplit; r.MM = t.MM; r.transpose = transpose ? 1 : 0;
         stats_.gram_flops += 8.0 * t.MM * t.MM * (double)t.CC;
@@ -1087,7 +1087,7 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
         const int nbz = std::min(65535, (int)grp.size() - off);
         dim3 grid(maxsplit, maxgroups, nbz);
 #define TNQS_DG(RT, I1) do { if (NW == 12) gram_dmma_kernel<RT, I1, 12><<<grid, 12 * 32, smem, stream_>>>(d + off); \
-                             else gram_dmma_kernel<RT, I1, 10><<<grid, 10 * 32, smem, stream_>>>(d + off); } while (0)
+                             else gram_dmma_kernel<RT, I1, 8><<<grid, 8 * 32, smem, stream_>>>(d + off); } while (0)
         if (c64()) { if (inner1) TNQS_DG(float, true); else TNQS_DG(float, false); }
         else { if (inner1) TNQS_DG(double, true); else TNQS_DG(double, false); }
 #undef TNQS_DG

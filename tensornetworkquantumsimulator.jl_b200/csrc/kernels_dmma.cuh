@@ -6,8 +6,8 @@
 // The complex Hermitian rank-K update is run as a REAL symmetric one: with the 2·MM real rows
 // W[(i,0)] = Re X[i], W[(i,1)] = Im X[i],  S = W·Wᵀ gives
 //     Re G[i][j] = S[(i,0),(j,0)] + S[(i,1),(j,1)],   Im G[i][j] = S[(i,0),(j,1)] − S[(i,1),(j,0)],
-// and only the 32×32 blocks of S on or below the diagonal are computed (10 of 16 for MM = 64), one
-// block per warp, 16 m8n8k4 accumulator tiles each.  A CTA streams its K-split of the tensor through
+// and only the 32×32 blocks of S on or below the diagonal are computed (10 of 16 for MM = 64; of the diagonal
+// blocks only the 8×8 tiles on or below THEIR diagonal), 16 m8n8k4 accumulator tiles per off-diagonal block.  A CTA streams its K-split of the tensor through
 // two shared-memory stages of KCH columns (chunk ch + 1 is converted to fp64 and stored while chunk ch is
 // multiplied, chunk ch + 2 is in flight from global memory).
 #pragma once
@@ -20,10 +20,14 @@ namespace tnqs {
 constexpr int DG_KCH = 32;            // columns per stage
 constexpr int DG_LD = DG_KCH + 4;     // row stride (doubles): rows land 32 B apart modulo 256 B → conflict-free fragment loads
 
-// Warps per CTA and staging registers per thread of the two instantiations: 10 warps for MM ≤ 64 (the 10 lower blocks of
-// a 128-row S), 12 warps for MM ≤ 128 (36 lower blocks of a 256-row S = 3 CTAs of 12; 12 warps also load the four SM
-// sub-partitions evenly: tools/dmma_probe.cu measures 30.1 TF/s with 10 resident warps, 36.2 with 12, peak 37.0).
-template <int NW> struct DgCfg { static constexpr int MAXPF = NW == 12 ? 11 : 7; };  // ≥ ⌈MM·KCH / (32·NW)⌉ (+ mapping padding)
+// Warps per CTA and staging registers per thread of the two instantiations.
+//   NW = 8, MM ≤ 64 (S has at most 4×4 blocks): one CTA covers all of S.  The 6 off-diagonal blocks take one warp each
+//   (16 tiles); the 4 diagonal blocks need only the 10 tiles on or below their own diagonal and their B fragments ARE
+//   their A fragments, so two of them share a warp (20 tiles, 4 fragment loads per block and k-step).  Two warps per SM
+//   sub-partition with 32 / 32 / 36 / 36 tiles per k-step instead of 3:3:2:2 warps of 16 (tools/dmma_probe.cu: the fp64
+//   pipe reaches 30.1 TF/s with 10 resident warps, 35.4 with 8, 36.2 with 12, peak 37.0), and 136 instead of 160 MMAs.
+//   NW = 12, MM ≤ 128: 36 lower blocks of a 256-row S = 3 CTAs of 12 warps, one block per warp.
+template <int NW> struct DgCfg { static constexpr int MAXPF = NW == 12 ? 11 : 8; };  // ≥ ⌈MM / NW⌉ (+ mapping padding)
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, const double a, const double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -55,16 +59,30 @@ __global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __re
   const int R32 = (rows + 31) / 32;
   const int nblk = R32 * (R32 + 1) / 2;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr bool PAIRED = NW == 8;  // diagonal blocks in pairs (see DgCfg)
   const int blk = blockIdx.y * NW + warp;
-  if (blockIdx.y * NW >= nblk) return;
-  // block (br, bc), br ≥ bc, enumerated row by row
+  if (PAIRED ? blockIdx.y > 0 : blockIdx.y * NW >= nblk) return;
+  // block (br, bc), br ≥ bc, enumerated row by row; PAIRED: off-diagonal blocks first, then pairs of diagonal blocks
   int br = 0, bc = 0;
-  {
+  bool active = blk < nblk, is_diag = false;
+  int ndd = 0;  // PAIRED diagonal warp: blocks (br, br) and, if ndd == 2, (br + 1, br + 1)
+  if (!PAIRED) {
     int b = blk < nblk ? blk : 0, r = 0;
     while (b >= r + 1) { b -= r + 1; ++r; }
     br = r; bc = b;
+  } else {
+    const int noff = R32 * (R32 - 1) / 2;
+    if (warp < noff) {
+      int b = warp, r = 1;
+      while (b >= r) { b -= r; ++r; }
+      br = r; bc = b; active = true;
+    } else {
+      is_diag = true;
+      br = bc = 2 * (warp - noff);
+      ndd = min(2, R32 - br);
+      active = ndd > 0;
+    }
   }
-  const bool active = blk < nblk;
   const int prow = R32 * 32;                 // padded rows held per stage
   double* stage0 = dg_smem;
   double* stage1 = dg_smem + (size_t)prow * DG_LD;
@@ -139,11 +157,11 @@ __global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __re
     }
   };
 
-  double acc[4][4][2];
+  // accumulator tiles: off-diagonal block: tile (a, b) at 4a + b; diagonal pair: block d, tile (a, b ≤ a) at 10d + a(a+1)/2 + b
+  constexpr int NACC = PAIRED ? 20 : 16;
+  double acc[NACC][2];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+  for (int q = 0; q < NACC; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
 
   // Software pipeline: while stage (ch & 1) is multiplied, chunk ch + 1 (already in registers) is converted and stored
   // into the other stage and chunk ch + 2 is requested from global memory; one barrier per chunk.  The stores and the
@@ -160,7 +178,7 @@ __global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __re
     double* st = (ch & 1) ? stage1 : stage0;
     if (ch + 1 < nchunk) sstore((ch & 1) ? stage0 : stage1);  // last read by the multiplication of chunk ch − 1, before the barrier
     if (ch + 2 < nchunk) gload(ch + 2);
-    if (active) {
+    if (active && !(PAIRED && is_diag)) {
       const double* arow = st + (size_t)(br * 32 + fr) * DG_LD + fk;
       const double* brow = st + (size_t)(bc * 32 + fr) * DG_LD + fk;
 #pragma unroll
@@ -173,7 +191,28 @@ __global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __re
 #pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
-          for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+          for (int b = 0; b < 4; ++b) dmma884(acc[4 * a + b][0], acc[4 * a + b][1], af[a], bf[b]);
+      }
+    } else if (PAIRED && active) {
+      // the B fragment of a row group has the same (row, k) ↔ lane mapping as its A fragment
+      const double* arow = st + (size_t)(br * 32 + fr) * DG_LD + fk;
+#pragma unroll
+      for (int ks = 0; ks < DG_KCH / 4; ++ks) {
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+          if (d < ndd) {
+            double af[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = arow[(size_t)(32 * d + 8 * a) * DG_LD + 4 * ks];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+              for (int b = 0; b <= a; ++b) {
+                const int q = (PAIRED ? 10 : 0) * d + a * (a + 1) / 2 + b;
+                dmma884(acc[q < NACC ? q : 0][0], acc[q < NACC ? q : 0][1], af[a], af[b]);
+              }
+          }
+        }
       }
     }
     __syncthreads();
@@ -181,22 +220,36 @@ __global__ void __launch_bounds__(NW * 32) gram_dmma_kernel(const GramTask* __re
   // ---- epilogue: S block → complex G entries ----------------------------------------------------------
   if (!active) return;
   double2* __restrict__ P = t.partial + (long long)split * MM * MM;
+  // this lane holds S[row][col], S[row][col+1] of tile (a, b) of block (rb, cb): row = rb·32 + 8a + fr = (i, part),
+  // col = cb·32 + 8b + 2·fk = (j, 0)
+  auto emit = [&](int rb, int cbk, int a, int b, double c0, double c1) {
+    const double d0 = __shfl_xor_sync(0xffffffffu, c0, 4);  // partner row (i, 1−part)
+    const double d1 = __shfl_xor_sync(0xffffffffu, c1, 4);
+    const int row = rb * 32 + 8 * a + fr;
+    if (row & 1) return;
+    const int i = row >> 1, j = (cbk * 32 + 8 * b + 2 * fk) >> 1;
+    if (i >= MM || j >= MM || j > i) return;  // on diagonal blocks keep the lower triangle only
+    double2 g; g.x = c0 + d1; g.y = c1 - d0;
+    P[(long long)i * MM + j] = g;
+    if (i != j) { double2 h; h.x = g.x; h.y = -g.y; P[(long long)j * MM + i] = h; }
+  };
+  if (!(PAIRED && is_diag)) {
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      // this lane: S[row][col], S[row][col+1] with row = br·32 + 8a + fr = (i, part), col = bc·32 + 8b + 2·fk = (j, 0)
-      const double c0 = acc[a][b][0], c1 = acc[a][b][1];
-      const double d0 = __shfl_xor_sync(0xffffffffu, c0, 4);  // partner row (i, 1−part)
-      const double d1 = __shfl_xor_sync(0xffffffffu, c1, 4);
-      const int row = br * 32 + 8 * a + fr;
-      if (row & 1) continue;
-      const int i = row >> 1, j = (bc * 32 + 8 * b + 2 * fk) >> 1;
-      if (i >= MM || j >= MM || j > i) continue;  // on diagonal blocks keep the lower triangle only
-      double2 g; g.x = c0 + d1; g.y = c1 - d0;
-      P[(long long)i * MM + j] = g;
-      if (i != j) { double2 h; h.x = g.x; h.y = -g.y; P[(long long)j * MM + i] = h; }
-    }
+      for (int b = 0; b < 4; ++b) emit(br, bc, a, b, acc[4 * a + b][0], acc[4 * a + b][1]);
+  } else {
+#pragma unroll
+    for (int d = 0; d < 2; ++d)
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b <= a; ++b) {
+          const int q = (PAIRED ? 10 : 0) * d + a * (a + 1) / 2 + b;
+          // every lane of the warp takes part in the shuffles of a tile; blocks past the matrix hold zeros and write nothing
+          if (d < ndd) emit(br + d, br + d, a, b, acc[q < NACC ? q : 0][0], acc[q < NACC ? q : 0][1]);
+        }
+  }
 }
 
 }  // namespace tnqs

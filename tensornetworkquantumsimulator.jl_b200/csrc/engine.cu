@@ -1901,10 +1901,12 @@ void Engine::apply_two_site_batch(const std::vector<int>& gate_ids, const int32_
         // preconditioned form, and only rank(θ) columns are non-zero) → V_K = Pᵀ·U_L ≈ right singular vectors →
         // B = θ·V_K has nearly orthogonal columns → a short Jacobi polish on B restores full relative accuracy.
         // Directions with σ < ~3e-8·σmax (σ² below the fp64 noise of K) come back as σ = 0, so the path is taken
-        // only when they cannot matter: ComplexF32 states (fp32 noise 6e-8) or a relative cutoff ≥ 1e-14 on σ².
+        // only when they cannot matter: ComplexF32 states (fp32 noise 6e-8) or a relative cutoff ≥ 1e-12 on σ² (a hundred
+        // such directions together stay below the cutoff, so neither the kept rank nor truncerr can depend on them).
         int maxcols_t = 0, maxrows_t = 0;
         for (auto& j : jt) { maxcols_t = std::max(maxcols_t, j.n); maxrows_t = std::max(maxrows_t, j.m); }
-        if (use_fast_svd_ && (c64() || ao.cutoff >= 1e-14) && maxcols_t <= 256 && maxrows_t <= 256 && maxcols_t >= 8) {
+        const bool tail_irrelevant = c64() || (ao.cutoff >= 1e-12 && ao.use_relative_cutoff && !ao.use_absolute_cutoff);
+        if (use_fast_svd_ && tail_irrelevant && maxcols_t <= 256 && maxrows_t <= 256 && maxcols_t >= 8) {
           std::vector<CholTask> ct(nm);
           std::vector<SmallGemmTask> g1(nm), g2(nm);
           std::vector<JacobiTask> jl(nm);

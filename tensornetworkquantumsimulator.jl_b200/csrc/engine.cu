@@ -1158,13 +1158,16 @@ void Engine::launch_gram(std::vector<GramTask>& tasks, bool acc_double, std::vec
   TNQS_CUDA(cudaGetLastError());
 }
 
-template <int LPP, int RPL, int MAXT, int MINB>
+template <int LPP, int RPL, int MAXT, int MINB, bool LOCALP>
 static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntasks, int BC, int C, int ld, size_t smem,
                                   double dead_rel2, double* nonconv, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+  // the shared-memory opt-in is a per-device attribute of the function
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    TNQS_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<LPP, RPL, MAXT, MINB, LOCALP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(ntasks * C));
@@ -1176,7 +1179,7 @@ static void launch_jacobi_cluster(const JacobiTask* d, JacobiAux* aux, int ntask
   at[0].val.clusterDim.x = (unsigned)C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   SlowLog sl("cudaLaunchKernelEx(jacobi)");
-  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2, nonconv));
+  TNQS_CUDA(cudaLaunchKernelEx(&cfg, jacobi_cluster_kernel<LPP, RPL, MAXT, MINB, LOCALP>, d, aux, BC, C, ld, 40, 8.9e-16, dead_rel2, nonconv));
 }
 
 void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
@@ -1224,9 +1227,14 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
     TNQS_CUDA(cudaMemsetAsync(aux, 0, sizeof(JacobiAux) * nb, stream_));
     // register budget: MINB CTAs of MAXT threads per SM
     const int thr = std::max(32, BC * LPP);
-#define TNQS_JAC(L, R) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
-    else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3)>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
-    else launch_jacobi_cluster<L, R, 512, 1>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); } while (0)
+    // launches that leave SMs idle are latency-bound: every lane group then computes its own rotation (one barrier per
+    // round, kernels_jacobi.cuh); TNQS_JACOBI_LOCALP=0/1 forces the choice
+    bool localp = (long long)nb * C <= 148;
+    if (const char* e = std::getenv("TNQS_JACOBI_LOCALP")) localp = std::atoi(e) != 0;
+#define TNQS_JAC2(L, R, P) do { if (thr <= 128) launch_jacobi_cluster<L, R, 128, (R >= 8 ? 4 : 6), P>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
+    else if (thr <= 256) launch_jacobi_cluster<L, R, 256, (R >= 8 ? 2 : 3), P>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); \
+    else launch_jacobi_cluster<L, R, 512, 1, P>(d, aux, (int)nb, BC, C, ld, smem, dead_rel2, d_errflags_, stream_); } while (0)
+#define TNQS_JAC(L, R) do { if (localp) TNQS_JAC2(L, R, true); else TNQS_JAC2(L, R, false); } while (0)
     bool launched = true;
     try {
       if (LPP == 16) {
@@ -1246,6 +1254,7 @@ void Engine::launch_jacobi(std::vector<JacobiTask>& tasks, double dead_rel2) {
       launched = false;
     }
 #undef TNQS_JAC
+#undef TNQS_JAC2
     if (launched) {
     count_launch();
     TNQS_CUDA(cudaGetLastError());

@@ -48,7 +48,13 @@ __device__ __forceinline__ void rr_pair(int ne, int step, int pair, int& p, int&
   else { p = (step + pair) % (ne - 1); q = (step - pair + (ne - 1)) % (ne - 1); }
 }
 
-template <int LPP, int RPL, int MAXT, int MINB>
+// LOCALP: every lane group computes the rotation of its own pair right after the dot products (all its lanes hold the
+// sums) and applies it at once: one barrier per round instead of three, and nobody waits for the one warp that otherwise
+// computes all rotation parameters (ncu, 18 matrices on the whole GPU: 60 % of the warp time at barriers, 22 % of all
+// samples behind that warp).  It repeats the fp64 rsqrt chains in every lane, which costs throughput when the SMs are
+// full (batching them was worth 1.25× there), so the host picks it only for launches that leave SMs idle — the sharded
+// run, small lattices.  Same operations per pair in the same order: the results are bit-identical.
+template <int LPP, int RPL, int MAXT, int MINB, bool LOCALP = false>
 __global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const JacobiTask* __restrict__ tasks, JacobiAux* __restrict__ aux,
                                                              int BC, int C, int ld, int max_sweeps, double tol,
                                                              double dead_rel2, double* __restrict__ nonconv) {
@@ -207,10 +213,39 @@ __global__ void __launch_bounds__(MAXT, MINB) jacobi_cluster_kernel(const Jacobi
               gx += __shfl_xor_sync(gmask, gx, o);
               gy += __shfl_xor_sync(gmask, gy, o);
             }
-            if (l == 0) { s_dot[pi][0] = a; s_dot[pi][1] = b; s_dot[pi][2] = gx; s_dot[pi][3] = gy; s_pair[pi][0] = s1; s_pair[pi][1] = s2; }
-          } else if (l == 0 && pi < BC) {
+            if (LOCALP) {
+              // phases B and C in place (same formulas as below)
+              const double g2 = gx * gx + gy * gy;
+              const bool alive_p = a > floor2, alive_q = b > floor2;
+              if (l == 0) { if (!alive_p) s_dead[s1] = 1; if (!alive_q) s_dead[s2] = 1; }
+              if (alive_p && alive_q && g2 > tol2 * a * b) {
+                if (l == 0) s_rot = 1;
+                const double dl = b - a;
+                const double ig = rsqrt(g2);
+                const double rh = rsqrt(dl * dl + 4.0 * g2);
+                const double c2 = 0.5 + 0.5 * fabs(dl) * rh;
+                const double rc = rsqrt(c2);
+                const double c = c2 * rc;
+                const double s = (dl >= 0 ? 1.0 : -1.0) * (g2 * ig) * rh * rc;
+                const double phx = gx * ig, phy = -gy * ig;
+#pragma unroll
+                for (int k = 0; k < RPL; ++k) {
+                  const double2 x = xr[k];
+                  double2 y;
+                  y.x = yr[k].x * phx - yr[k].y * phy;
+                  y.y = yr[k].x * phy + yr[k].y * phx;
+                  double2 xn, yn;
+                  xn.x = c * x.x - s * y.x; xn.y = c * x.y - s * y.y;
+                  yn.x = s * x.x + c * y.x; yn.y = s * x.y + c * y.y;
+                  if (xres) xr[k] = xn; else cp[l + LPP * k] = xn;
+                  cq[l + LPP * k] = yn;
+                }
+              }
+            } else if (l == 0) { s_dot[pi][0] = a; s_dot[pi][1] = b; s_dot[pi][2] = gx; s_dot[pi][3] = gy; s_pair[pi][0] = s1; s_pair[pi][1] = s2; }
+          } else if (!LOCALP && l == 0 && pi < BC) {
             s_pair[pi][0] = -1;
           }
+          if (LOCALP) { __syncthreads(); continue; }  // the rotated columns are visible to the next round's pairing
           if (!__syncthreads_or(live ? 1 : 0)) continue;  // nothing alive in this round
           // ---- phase B: one warp turns the BC dot products into rotations (the fp64 rsqrt chains are
           //      issued once per round instead of once per lane group) ---------------------------------------
